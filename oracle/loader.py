@@ -78,16 +78,16 @@ class _Base:
         radii = _f32(radii)
         self._keep.append((pts, radii))
         self._n.append(pts.shape[0])
-        return self._fn("add_point_set", C.c_int, C.c_void_p, _fp, _fp, C.c_int)(
-            self.h, _ptr(pts, _fp), _ptr(radii, _fp), pts.shape[0])
+        return self._fn("add_point_set", C.c_int, C.c_void_p, _fp, _fp, C.c_int, C.c_int)(
+            self.h, _ptr(pts, _fp), _ptr(radii, _fp), pts.shape[0], int(radii is not None))
 
     def resize_point_set(self, s, pts, radii=None):
         pts = _f32(pts).reshape(-1, 3)
         radii = _f32(radii)
         self._keep.append((pts, radii))
         self._n[s] = pts.shape[0]
-        self._fn("resize_point_set", None, C.c_void_p, C.c_int, _fp, _fp, C.c_int)(
-            self.h, s, _ptr(pts, _fp), _ptr(radii, _fp), pts.shape[0])
+        self._fn("resize_point_set", None, C.c_void_p, C.c_int, _fp, _fp, C.c_int, C.c_int)(
+            self.h, s, _ptr(pts, _fp), _ptr(radii, _fp), pts.shape[0], int(radii is not None))
 
     def set_search_radius(self, r):
         self._fn("set_search_radius", None, C.c_void_p, C.c_float)(self.h, float(r))
@@ -186,8 +186,8 @@ class Reference(_Base):
         radii = None if radii is None else np.ascontiguousarray(radii, dtype=np.float64)
         self._keep.append((pts, radii))
         self._n.append(pts.shape[0])
-        return self._fn("add_point_set_f64", C.c_int, C.c_void_p, _dp, _dp, C.c_int)(
-            self.h, _ptr(pts, _dp), _ptr(radii, _dp), pts.shape[0])
+        return self._fn("add_point_set_f64", C.c_int, C.c_void_p, _dp, _dp, C.c_int, C.c_int)(
+            self.h, _ptr(pts, _dp), _ptr(radii, _dp), pts.shape[0], int(radii is not None))
 
     def set_n_threads(self, n):
         self._fn("set_n_threads", None, C.c_void_p, C.c_int)(self.h, int(n))

@@ -29,6 +29,7 @@ struct RefCtx {
     std::vector<int> n;
     std::vector<const float*> pts;
     std::vector<const float*> radii;
+    std::vector<int> variable;
     float radius = -1.0f;
     int last_mode = 0;
     bool bf_built = false;
@@ -49,25 +50,27 @@ void tnsref_set_search_radius(void* h, float r)
     c->tns.set_search_radius(r);
 }
 
-int tnsref_add_point_set(void* h, const float* pts, const float* radii, int n)
+/* `variable` selects the overload with a radii array (an empty variable-radius set is (nullptr, nullptr, 0), tests/tests.cpp:369) */
+int tnsref_add_point_set(void* h, const float* pts, const float* radii, int n, int variable)
 {
     auto* c = static_cast<RefCtx*>(h);
-    c->n.push_back(n); c->pts.push_back(pts); c->radii.push_back(radii);
-    return radii ? c->tns.add_point_set(pts, radii, n) : c->tns.add_point_set(pts, n);
+    c->n.push_back(n); c->pts.push_back(pts); c->radii.push_back(radii); c->variable.push_back(variable);
+    return variable ? c->tns.add_point_set(pts, radii, n) : c->tns.add_point_set(pts, n);
 }
 
-int tnsref_add_point_set_f64(void* h, const double* pts, const double* radii, int n)
+int tnsref_add_point_set_f64(void* h, const double* pts, const double* radii, int n, int variable)
 {
     auto* c = static_cast<RefCtx*>(h);
-    c->n.push_back(n); c->pts.push_back(nullptr); c->radii.push_back(nullptr);
-    return radii ? c->tns.add_point_set(pts, radii, n) : c->tns.add_point_set(pts, n);
+    c->n.push_back(n); c->pts.push_back(nullptr); c->radii.push_back(nullptr); c->variable.push_back(variable);
+    return variable ? c->tns.add_point_set(pts, radii, n) : c->tns.add_point_set(pts, n);
 }
 
-void tnsref_resize_point_set(void* h, int s, const float* pts, const float* radii, int n)
+void tnsref_resize_point_set(void* h, int s, const float* pts, const float* radii, int n, int variable)
 {
     auto* c = static_cast<RefCtx*>(h);
-    c->n[s] = n; c->pts[s] = pts; c->radii[s] = radii;
-    if (radii) c->tns.resize_point_set(s, pts, radii, n); else c->tns.resize_point_set(s, pts, n);
+    c->n[s] = n; c->pts[s] = pts;
+    if (variable) { c->radii[s] = radii; c->tns.resize_point_set(s, pts, radii, n); }
+    else c->tns.resize_point_set(s, pts, n);
 }
 
 void tnsref_set_active_search(void* h, int i, int j, int b) { static_cast<RefCtx*>(h)->tns.set_active_search(i, j, b != 0); }
@@ -80,8 +83,8 @@ static void build_bf(RefCtx* c)
     c->bf = BruteforceNSearch();
     const int ns = c->tns.get_n_sets();
     for (int s = 0; s < ns; s++) {
-        if (c->radii[s]) c->bf.add_point_set(c->pts[s], c->radii[s], c->n[s]);
-        else             c->bf.add_point_set(c->pts[s], c->radius, c->n[s]);
+        if (c->variable[s]) c->bf.add_point_set(c->pts[s], c->radii[s], c->n[s]);
+        else                c->bf.add_point_set(c->pts[s], c->radius, c->n[s]);
     }
     for (int i = 0; i < ns; i++)
         for (int j = 0; j < ns; j++)

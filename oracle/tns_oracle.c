@@ -44,7 +44,8 @@
 typedef struct {
     int          n_sets;
     const float *pts[TNSO_MAX_SETS];
-    const float *radii[TNSO_MAX_SETS];      /* NULL in fixed radius mode */
+    const float *radii[TNSO_MAX_SETS];      /* per-point radii (variable radius mode) */
+    int          variable[TNSO_MAX_SETS];   /* set was added through the overload with a radii array */
     int          n[TNSO_MAX_SETS];
     float        radius;                    /* fixed radius, < 0 if not set */
     int          symmetric;                 /* default 1: TreeNSearch.h:385 */
@@ -97,19 +98,20 @@ void tnso_destroy(void *h)
     free(o);
 }
 
-int tnso_add_point_set(void *h, const float *pts, const float *radii, int n)
+int tnso_add_point_set(void *h, const float *pts, const float *radii, int n, int variable)
 {
     tnso_t *o = (tnso_t *)h;
     if (o->n_sets >= TNSO_MAX_SETS) return -1;
     const int s = o->n_sets++;
-    o->pts[s] = pts; o->radii[s] = radii; o->n[s] = n;
+    o->pts[s] = pts; o->radii[s] = variable ? radii : NULL; o->n[s] = n; o->variable[s] = variable;
     return s;
 }
 
-void tnso_resize_point_set(void *h, int s, const float *pts, const float *radii, int n)
+void tnso_resize_point_set(void *h, int s, const float *pts, const float *radii, int n, int variable)
 {
     tnso_t *o = (tnso_t *)h;
-    o->pts[s] = pts; o->radii[s] = radii; o->n[s] = n;
+    o->pts[s] = pts; o->n[s] = n;
+    if (variable) o->radii[s] = radii;       /* the overload without radii keeps the old pointer, TreeNSearch.cpp:97-121 */
 }
 
 void tnso_set_search_radius(void *h, float r) { ((tnso_t *)h)->radius = r; }
@@ -294,8 +296,8 @@ int tnso_run(void *h, int mode)
     tnso_free_results(o);
     const int fixed = o->radius >= 0.0f;
     for (int s = 0; s < o->n_sets; s++) {
-        if (fixed && o->radii[s]) return -1;              /* TreeNSearch.cpp:383-386 */
-        if (!fixed && !o->radii[s] && o->n[s] > 0) return -2;   /* TreeNSearch.cpp:388-391 */
+        if (fixed && o->variable[s]) return -1;           /* TreeNSearch.cpp:383-386 */
+        if (!fixed && !o->variable[s]) return -2;         /* TreeNSearch.cpp:388-391 */
     }
     if (mode == 0) {
         for (int si = 0; si < o->n_sets; si++)

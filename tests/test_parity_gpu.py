@@ -1,0 +1,397 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (via the Python mirror of the reference class),
+against the restated oracle, the golden fixtures generated from the unmodified reference and -- when oracle/_ref travelled
+with the snapshot -- the reference itself.  Bar: bit-exact integer index sets per (set_i, set_j, i)."""
+import numpy as np
+import pytest
+
+import cases
+from conftest import csr_equal
+from oracle import loader
+from treensearch_b200 import clouds
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tnsb(built_library):
+    import treensearch_b200 as t
+    return t
+
+
+def run_engine(t, case, f64_sets=(), options=None):
+    eng = t.TreeNSearch()
+    for k, v in (options or {}).items():
+        eng.set_option(k, v)
+    if case["radius"] is not None:
+        eng.set_search_radius(case["radius"])
+    for s, (p, r) in enumerate(case["sets"]):
+        if s in f64_sets:
+            p = p.astype(np.float64)
+            r = None if r is None else r.astype(np.float64)
+        eng.add_point_set(p, r, variable_radius=(case["radius"] is None))
+        eng._test_keep = getattr(eng, "_test_keep", []) + [(p, r)]
+    for (i, j) in case["pairs"]:
+        eng.set_active_search(i, j, True)
+    eng.set_symmetric_search(case["symmetric"])
+    eng.run()
+    return eng
+
+
+def assert_matches_port(eng, case, pairs=None):
+    port = cases.configure(loader.OraclePort(), case)
+    port.run(1)
+    for p in (pairs or case["pairs"]):
+        a = eng.neighbor_csr(*p)
+        b = port.csr(*p)
+        assert np.array_equal(a[0], b[0]), f"pair {p}: neighbour counts differ"
+        assert np.array_equal(a[1], b[1]), f"pair {p}: neighbour ids differ"
+
+
+# ---------------------------------------------------------------------------------------------------- golden fixtures
+@pytest.mark.parametrize("name", list(cases.GOLDEN_CASES))
+def test_golden(tnsb, golden, name):
+    case = cases.GOLDEN_CASES[name]()
+    eng = run_engine(tnsb, case)
+    for (i, j) in case["pairs"]:
+        off, idx = eng.neighbor_csr(i, j)
+        assert np.array_equal(off, golden[f"{name}/{i}_{j}/offsets"]), (name, i, j)
+        assert np.array_equal(idx, golden[f"{name}/{i}_{j}/indices"]), (name, i, j)
+
+
+def test_neighborlist_handle_layout(tnsb):
+    # NeighborList is a view of [n, j0, j1 ...] (NeighborList.h:8-39): size() is the word in front of the ids
+    case = cases.GOLDEN_CASES["lattice_fixed_100"]()
+    eng = run_engine(tnsb, case)
+    ragged, pos = eng.neighbor_lists(0, 0)
+    for i in (0, 7, 124):
+        nl = eng.get_neighborlist(0, 0, i)
+        assert nl.size() == ragged[pos[i]] == len(list(nl))
+        got = []
+        eng.for_each_neighbor(0, 0, i, got.append)
+        assert got == list(nl)
+        assert i not in got
+    assert eng.get_neighborlist_n_bytes() == 4 * ragged.shape[0]
+
+
+# ---------------------------------------------------------------------------------------------------- reference test cases
+@pytest.mark.parametrize("n", [1, 100, 10000])
+def test_one_set_fixed_radius(tnsb, n):            # tests/tests.cpp:91-112
+    pts, r = clouds.sph_lattice(n)
+    case = dict(sets=[(pts, None)], radius=float(r), pairs=[(0, 0)], symmetric=True)
+    assert_matches_port(run_engine(tnsb, case), case)
+
+
+@pytest.mark.parametrize("n", [1, 100, 10000])
+def test_two_dynamic_sets_variable_radius(tnsb, n):   # tests/tests.cpp:114-145
+    case = cases._lattice_two_sets(n)
+    eng = run_engine(tnsb, case)
+    assert_matches_port(eng, case)
+    assert not eng.is_search_active(1, 1)
+    with pytest.raises(tnsb.TreeNSearchError):
+        eng.neighbor_lists(1, 1)
+
+
+@pytest.mark.parametrize("n", [100, 10000])
+def test_mixed_float_double_point_sets(tnsb, n):      # tests/tests.cpp:147-186
+    case = cases._lattice_two_sets(n, 1.33)
+    assert_matches_port(run_engine(tnsb, case, f64_sets=(1,)), case)
+    assert_matches_port(run_engine(tnsb, case, f64_sets=(0, 1)), case)
+
+
+def test_resize_variable_radius(tnsb):                # tests/tests.cpp:188-237
+    full = cases._lattice_two_sets(10000)
+    (p0, r0), (p1, r1) = full["sets"]
+    eng = tnsb.TreeNSearch()
+    eng.add_point_set(p0, r0, n_points=p0.shape[0] // 2)
+    eng.add_point_set(p1, r1, n_points=p1.shape[0] // 2)
+    for p in full["pairs"]:
+        eng.set_active_search(*p, True)
+    for frac in (2, 1, 3):
+        n0, n1 = p0.shape[0] // frac, p1.shape[0] // frac
+        eng.resize_point_set(0, p0, r0, n_points=n0)
+        eng.resize_point_set(1, p1, r1, n_points=n1)
+        eng.run()
+        assert eng.get_n_points_in_set(0) == n0 and eng.get_total_n_points() == n0 + n1
+        sub = dict(full, sets=[(p0[:n0], r0[:n0]), (p1[:n1], r1[:n1])])
+        assert_matches_port(eng, sub)
+
+
+def test_dynamic_emitter_style_sequence(tnsb):       # tests/tests.cpp:434-514 (shortened): add / remove / replace with empty sets
+    rs = np.random.RandomState(123)
+    eng = tnsb.TreeNSearch()
+    empty = np.zeros((0, 3), np.float32)
+    for _ in range(2):
+        eng.add_point_set(empty, np.zeros(0, np.float32))
+    eng.set_all_searches(True)
+    store = [None, None]
+    sizes = [0, 0]
+    for it in range(40):
+        s = int(rs.randint(0, 2))
+        action = int(rs.randint(0, 3))
+        amount = int(rs.randint(1, 21))
+        sizes[s] = sizes[s] + amount if action == 0 else (max(0, sizes[s] - amount) if action == 1 else amount)
+        p = (rs.random_sample((sizes[s], 3)) * 10.0).astype(np.float32)
+        r = np.full(sizes[s], 0.5, np.float32)
+        store[s] = (p, r)
+        eng.resize_point_set(s, p, r)
+        eng.run()
+        sets = [st if st is not None else (empty, np.zeros(0, np.float32)) for st in store]
+        case = dict(sets=sets, radius=None, pairs=[(0, 0), (0, 1), (1, 0), (1, 1)], symmetric=True)
+        assert_matches_port(eng, case)
+
+
+# ---------------------------------------------------------------------------------------------------- configs of BASELINE.json
+def test_c1_100k_uniform(tnsb):
+    n = 100_000
+    pts = clouds.uniform_cloud(n, 42)
+    case = dict(sets=[(pts, None)], radius=float(clouds.radius_for_mean_neighbors(n)), pairs=[(0, 0)], symmetric=True)
+    eng = run_engine(tnsb, case)
+    a = eng.neighbor_csr(0, 0)
+    assert a[0][-1] == 2864970
+    assert_matches_port(eng, case)
+    if loader.reference_available():
+        ref = cases.configure(loader.Reference(), case)
+        ref.run(0)
+        assert csr_equal(a, ref.csr(0, 0))
+        ref.run(2)                                   # BruteforceNSearch, ~6 s on 8 cores
+        assert csr_equal(a, ref.csr(0, 0))
+
+
+def _digest_compare(eng, pair, ref_off, ref_idx):
+    ragged, pos = eng.neighbor_lists(*pair)
+    cnt = ragged[pos]
+    assert np.array_equal(cnt.astype(np.int64), np.diff(ref_off)), "neighbour counts differ"
+    mine = loader.list_digests(ragged, pos + 1, cnt)
+    theirs = loader.csr_digests(ref_off, ref_idx)
+    bad = np.nonzero(mine != theirs)[0]
+    assert bad.size == 0, f"{bad.size} neighbour lists differ, first at point {bad[:5]}"
+
+
+def test_c2_10m_uniform(tnsb):
+    n = 10_000_000
+    pts = clouds.uniform_cloud(n, 42)
+    r = clouds.radius_for_mean_neighbors(n)
+    case = dict(sets=[(pts, None)], radius=float(r), pairs=[(0, 0)], symmetric=True)
+    eng = run_engine(tnsb, case)
+    st = eng.stats()
+    assert st["n_neighbors"] == 296973820            # K at 10M, seed 42
+    port = cases.configure(loader.OraclePort(), case)
+    port.run(1)
+    _digest_compare(eng, (0, 0), *port.csr(0, 0))
+    if loader.reference_available():
+        ref = cases.configure(loader.Reference(), case)
+        ref.run(0)
+        _digest_compare(eng, (0, 0), *ref.csr(0, 0, sort_lists=False))
+    # idempotence: a second run on the same data gives the same sets
+    ragged, pos = eng.neighbor_lists(0, 0)
+    d1 = loader.list_digests(ragged, pos + 1, ragged[pos])
+    eng.run()
+    ragged, pos = eng.neighbor_lists(0, 0)
+    assert np.array_equal(d1, loader.list_digests(ragged, pos + 1, ragged[pos]))
+
+
+def test_c3_dam_break_with_zsort(tnsb):
+    n = 2_000_000
+    pts, d, r = clouds.dam_break_cloud(n)
+    pts = pts.copy()
+    eng = tnsb.TreeNSearch()
+    eng.set_search_radius(float(r))
+    eng.add_point_set(pts)
+    eng.set_active_search(0, 0, True)
+    for step in range(3):
+        if step % 2 == 0:
+            eng.prepare_zsort()
+            eng.apply_zsort(0, pts, 3)
+        eng.run()
+        case = dict(sets=[(pts, None)], radius=float(r), pairs=[(0, 0)], symmetric=True)
+        port = cases.configure(loader.OraclePort(), case)
+        port.run(1)
+        _digest_compare(eng, (0, 0), *port.csr(0, 0))
+        pts[...] = clouds.advect(pts, d, step)
+    assert eng.stats()["n_neighbors"] / n > 40
+
+
+def test_c4_two_sets_variable_radii(tnsb):
+    p0, r0, p1, r1, _ = clouds.two_set_cloud(400_000, 100_000)
+    for sym in (True, False):
+        case = dict(sets=[(p0, r0), (p1, r1)], radius=None, pairs=[(0, 0), (0, 1), (1, 0)], symmetric=sym)
+        eng = run_engine(tnsb, case)
+        port = cases.configure(loader.OraclePort(), case)
+        port.run(1)
+        for p in case["pairs"]:
+            _digest_compare(eng, p, *port.csr(*p))
+
+
+# ---------------------------------------------------------------------------------------------------- engine behaviour
+def test_empty_inputs(tnsb):
+    eng = tnsb.TreeNSearch()
+    eng.set_search_radius(0.1)
+    eng.add_point_set(np.zeros((0, 3), np.float32))
+    eng.set_active_search(0, 0, True)
+    eng.run()
+    ragged, pos = eng.neighbor_lists(0, 0)
+    assert ragged.shape[0] == 0 and pos.shape[0] == 0
+    eng.prepare_zsort()
+    assert eng.get_zsort_order(0).shape[0] == 0
+    # no sets at all
+    eng2 = tnsb.TreeNSearch()
+    eng2.set_search_radius(0.1)
+    eng2.run()
+    assert eng2.get_n_sets() == 0 and eng2.get_total_n_points() == 0
+
+
+def test_64bit_keys_sparse_domain(tnsb):
+    # radius tiny against the extent: > 1024 cells per axis -> 63-bit Morton keys
+    rs = np.random.RandomState(4)
+    centers = (rs.random_sample((300, 3)) * 100.0).astype(np.float32)
+    pts = np.ascontiguousarray((centers[:, None, :] + 0.02 * rs.standard_normal((300, 20, 3)).astype(np.float32)).reshape(-1, 3))
+    case = dict(sets=[(pts, None)], radius=0.03, pairs=[(0, 0)], symmetric=True)
+    eng = run_engine(tnsb, case)
+    assert eng.stats()["key_bits"] > 30
+    assert_matches_port(eng, case)
+
+
+def test_long_lists_and_dense_cells(tnsb):
+    # one list longer than the per-warp staging buffer (> 2047 ids) and candidate lists longer than the register path
+    rs = np.random.RandomState(8)
+    blob = (0.5 + 0.002 * rs.standard_normal((2600, 3))).astype(np.float32)
+    bg = rs.random_sample((3000, 3)).astype(np.float32)
+    pts = np.ascontiguousarray(np.concatenate([blob, bg]))
+    case = dict(sets=[(pts, None)], radius=0.04, pairs=[(0, 0)], symmetric=True)
+    eng = run_engine(tnsb, case)
+    assert eng.stats()["n_neighbors"] > 2600 * 2500
+    assert_matches_port(eng, case)
+
+
+def test_list_buffer_overflow_rerun(tnsb):
+    case = cases.GOLDEN_CASES["uniform_fixed_5000"]()
+    eng = run_engine(tnsb, case, options={tnsb.TNSB_OPT_LIST_CAPACITY: 1})
+    assert eng.stats()["n_reruns"] >= 1
+    assert_matches_port(eng, case)
+
+
+def test_sorted_lists_option(tnsb):
+    case = cases.GOLDEN_CASES["clustered_blob"]()
+    eng = run_engine(tnsb, case, options={tnsb.TNSB_OPT_SORT_LISTS: 1})
+    ragged, pos = eng.neighbor_lists(0, 0)
+    off, idx = eng.neighbor_csr(0, 0, sort_lists=False)      # stored order
+    port = cases.configure(loader.OraclePort(), case)
+    port.run(1)
+    assert csr_equal((off, idx), port.csr(0, 0))            # ascending exactly like the reference's lists
+
+
+def test_query_limit_halo_points(tnsb):
+    # points with index >= limit are find-only (halo of a Z-slab shard): the first `limit` lists equal the full search
+    case = cases.GOLDEN_CASES["uniform_fixed_5000"]()
+    eng = run_engine(tnsb, case, options={tnsb.TNSB_OPT_QUERY_LIMIT: 3000})
+    off, idx = eng.neighbor_csr(0, 0)
+    port = cases.configure(loader.OraclePort(), case)
+    port.run(1)
+    poff, pidx = port.csr(0, 0)
+    assert off.shape[0] == 3001
+    assert np.array_equal(off, poff[:3001]) and np.array_equal(idx, pidx[: poff[3000]])
+
+
+def test_device_resident_io(tnsb):
+    import torch
+    case = cases.GOLDEN_CASES["uniform_fixed_5000"]()
+    pts = torch.from_numpy(case["sets"][0][0]).cuda()
+    eng = tnsb.TreeNSearch()
+    eng.set_option(tnsb.TNSB_OPT_HOST_RESULTS, 0)
+    eng.set_search_radius(case["radius"])
+    eng.add_point_set(pts)
+    eng.set_active_search(0, 0, True)
+    eng.run()
+    st = eng.stats()
+    assert st["h2d_bytes"] == 0 and st["d2h_bytes"] == 0
+    with pytest.raises(tnsb.TreeNSearchError):
+        eng.neighbor_lists(0, 0)
+    d_ragged, d_pos, n_ints = eng.neighbor_lists_device(0, 0)
+    assert n_ints == st["n_list_ints"] == st["n_neighbors"] + 5000
+    # pinned host input takes the same path as pageable input
+    pinned = torch.from_numpy(case["sets"][0][0]).pin_memory()
+    eng2 = tnsb.TreeNSearch()
+    eng2.set_search_radius(case["radius"])
+    eng2.add_point_set(pinned)
+    eng2.set_active_search(0, 0, True)
+    eng2.run()
+    assert eng2.stats()["n_neighbors"] == st["n_neighbors"]
+    assert_matches_port(eng2, case)
+
+
+def test_zsort_permutation_and_rerun(tnsb):
+    pts = clouds.uniform_cloud(50_000, 17).copy()
+    vel = np.arange(50_000, dtype=np.float32)
+    r = float(clouds.radius_for_mean_neighbors(50_000))
+    eng = tnsb.TreeNSearch()
+    eng.set_search_radius(r)
+    eng.add_point_set(pts)
+    eng.set_active_search(0, 0, True)
+    eng.prepare_zsort()                                  # no run() yet: from scratch (TreeNSearch.cpp:2592-2595)
+    order = eng.get_zsort_order(0).copy()
+    assert np.array_equal(np.sort(order), np.arange(50_000))
+    before = pts.copy()
+    eng.apply_zsort(0, pts, 3)
+    eng.apply_zsort(0, vel, 1)
+    assert np.array_equal(pts, before[order]) and np.array_equal(vel, order.astype(np.float32))
+    # the new order is a Z-order: Morton keys of the grid cells are non-decreasing
+    st_cell = r * (1.0 + 1.0 / 8192.0)
+    eng.run()
+    st = eng.stats()
+    cell = np.floor((pts.astype(np.float64) - np.array(st["domain_bottom"], np.float64)) / st_cell).astype(np.int64)
+    keys = np.array([loader.morton3d_64(*c) for c in cell[::97]], dtype=np.uint64)
+    assert np.all(np.diff(keys.astype(np.int64)) >= 0)
+    case = dict(sets=[(pts, None)], radius=r, pairs=[(0, 0)], symmetric=True)
+    assert_matches_port(eng, case)
+    # after a run the order comes from the existing grid (TreeNSearch.cpp:2598-2661); sorted data -> identity-like order
+    eng.prepare_zsort()
+    order2 = eng.get_zsort_order(0)
+    assert np.array_equal(np.sort(order2), np.arange(50_000))
+    assert np.array_equal(order2, np.arange(50_000))     # stable sort of already Z-sorted data is the identity
+
+
+def test_error_behaviour(tnsb):
+    pts = clouds.uniform_cloud(100, 1)
+    rad = np.full(100, 0.1, np.float32)
+    eng = tnsb.TreeNSearch()
+    eng.add_point_set(pts, rad)
+    with pytest.raises(tnsb.TreeNSearchError, match="Cannot set a global search radius"):      # TreeNSearch.cpp:22-25
+        eng.set_search_radius(0.1)
+    eng = tnsb.TreeNSearch()
+    eng.add_point_set(pts)
+    eng.set_active_search(0, 0, True)
+    with pytest.raises(tnsb.TreeNSearchError, match="not all point sets have per-point search radius"):   # :388-391
+        eng.run()
+    eng = tnsb.TreeNSearch()
+    eng.set_search_radius(-1.0)
+    eng.add_point_set(pts)
+    with pytest.raises(tnsb.TreeNSearchError, match="global_search_radius <= 0"):               # :378-381
+        eng.run()
+    eng = tnsb.TreeNSearch()
+    eng.set_cell_size(0.5)
+    with pytest.raises(tnsb.TreeNSearchError, match="Cell size already set"):                   # :175-178
+        eng.set_cell_size(0.6)
+    with pytest.raises(tnsb.TreeNSearchError, match="Cannot resize a set that was not previously added"):   # :69-72
+        eng.resize_point_set(3, pts)
+    eng = tnsb.TreeNSearch()
+    eng.set_search_radius(0.1)
+    eng.add_point_set(pts)
+    with pytest.raises(tnsb.TreeNSearchError, match="previously didn't have one"):              # :73-76
+        eng.resize_point_set(0, pts, rad)
+
+
+def test_set_active_search_overloads(tnsb):
+    pts = clouds.uniform_cloud(10, 1)
+    eng = tnsb.TreeNSearch()
+    eng.set_search_radius(0.5)
+    for _ in range(3):
+        eng.add_point_set(pts)
+    eng.set_active_search(1, True, False)        # set 1 searches in all, is found by none (TreeNSearch.cpp:225-235)
+    table = [[eng.is_search_active(i, j) for j in range(3)] for i in range(3)]
+    assert table == [[False, False, False], [True, True, True], [False, False, False]]
+    eng.set_active_search(1, False, True)        # order matters: the search row overwrites (1,1)
+    table = [[eng.is_search_active(i, j) for j in range(3)] for i in range(3)]
+    assert table == [[False, True, False], [False, False, False], [False, True, False]]
+    eng.set_all_searches(True)
+    assert all(eng.is_search_active(i, j) for i in range(3) for j in range(3))
+    assert eng.does_set_exist(2) and not eng.does_set_exist(3)

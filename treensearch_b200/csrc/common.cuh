@@ -1,0 +1,124 @@
+// common.cuh -- shared device helpers of the B200 neighbour-search engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tnsb {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// grid geometry shared by key generation and the query (device copy lives in constant-like kernel arguments)
+struct GridParams {
+    double bottom[3];   // world box origin (double: cell coordinates are computed in fp64 so that the stencil argument holds
+    double inv_cell;    //                   for any grid resolution, see DESIGN.md "candidate completeness")
+    int    bits;        // Morton bits per dimension (cells per dimension = 1 << bits)
+    int    max_coord;   // (1 << bits) - 1
+};
+
+__host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- Morton codes, libmorton bit order (x -> bit 0, y -> bit 1, z -> bit 2; reference: extern/libmorton/morton_BMI.h:40-52)
+__host__ __device__ __forceinline__ uint32_t expand_bits_10(uint32_t v)
+{
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__host__ __device__ __forceinline__ uint32_t compact_bits_10(uint32_t v)
+{
+    v &= 0x09249249u;
+    v = (v | (v >> 2)) & 0x030c30c3u;
+    v = (v | (v >> 4)) & 0x0300f00fu;
+    v = (v | (v >> 8)) & 0x030000ffu;
+    v = (v | (v >> 16)) & 0x3ffu;
+    return v;
+}
+__host__ __device__ __forceinline__ uint64_t expand_bits_21(uint64_t v)
+{
+    v &= 0x1fffffull;
+    v = (v | (v << 32)) & 0x001f00000000ffffull;
+    v = (v | (v << 16)) & 0x001f0000ff0000ffull;
+    v = (v | (v << 8)) & 0x100f00f00f00f00full;
+    v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+    v = (v | (v << 2)) & 0x1249249249249249ull;
+    return v;
+}
+__host__ __device__ __forceinline__ uint32_t compact_bits_21(uint64_t v)
+{
+    v &= 0x1249249249249249ull;
+    v = (v | (v >> 2)) & 0x10c30c30c30c30c3ull;
+    v = (v | (v >> 4)) & 0x100f00f00f00f00full;
+    v = (v | (v >> 8)) & 0x001f0000ff0000ffull;
+    v = (v | (v >> 16)) & 0x001f00000000ffffull;
+    v = (v | (v >> 32)) & 0x1fffffull;
+    return (uint32_t)v;
+}
+
+template <typename Key> struct Morton;
+template <> struct Morton<uint32_t> {
+    static constexpr int kMaxBits = 10;
+    static constexpr uint32_t kEmpty = 0xffffffffu;
+    __host__ __device__ static __forceinline__ uint32_t encode(uint32_t x, uint32_t y, uint32_t z)
+    {
+        return expand_bits_10(x) | (expand_bits_10(y) << 1) | (expand_bits_10(z) << 2);
+    }
+    __host__ __device__ static __forceinline__ void decode(uint32_t k, int& x, int& y, int& z)
+    {
+        x = (int)compact_bits_10(k); y = (int)compact_bits_10(k >> 1); z = (int)compact_bits_10(k >> 2);
+    }
+    __host__ __device__ static __forceinline__ uint32_t hash(uint32_t k) { return k * 0x9E3779B1u; }
+};
+template <> struct Morton<uint64_t> {
+    static constexpr int kMaxBits = 21;
+    static constexpr uint64_t kEmpty = 0xffffffffffffffffull;
+    __host__ __device__ static __forceinline__ uint64_t encode(uint32_t x, uint32_t y, uint32_t z)
+    {
+        return expand_bits_21(x) | (expand_bits_21(y) << 1) | (expand_bits_21(z) << 2);
+    }
+    __host__ __device__ static __forceinline__ void decode(uint64_t k, int& x, int& y, int& z)
+    {
+        x = (int)compact_bits_21(k); y = (int)compact_bits_21(k >> 1); z = (int)compact_bits_21(k >> 2);
+    }
+    __host__ __device__ static __forceinline__ uint32_t hash(uint64_t k)
+    {
+        return (uint32_t)((k * 0x9E3779B97F4A7C15ull) >> 32);
+    }
+};
+
+// ---- order preserving float <-> uint mapping for atomic min / max
+__device__ __forceinline__ uint32_t float_to_ordered(float f)
+{
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ordered_to_float(uint32_t o)
+{
+    const uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+
+__device__ __forceinline__ unsigned lanemask_lt()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// streaming (read-once) loads / write-once stores: keep them out of L1 so the query's candidate tiles stay cached
+__device__ __forceinline__ float4 ld_nc_f4(const float4* p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+}  // namespace tnsb

@@ -1,0 +1,194 @@
+// grid_build.cuh -- everything between the raw point arrays and the sorted uniform grid:
+//   world box + radius reduction      (replaces _update_world_AABB[_simd],  TreeNSearch.cpp:415-645)
+//   cell assignment + Morton keys      (replaces _points_to_cells[_simd],    TreeNSearch.cpp:646-1113, and libmorton)
+//   reorder gather into sorted float4  (replaces the leaf gather,            TreeNSearch.cpp:2161-2399)
+//   cell start/end compaction + hash   (replaces CellList,                   internals/octree_internals.h:63-159)
+#pragma once
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace tnsb {
+
+// ----------------------------------------------------------------------------------------------------------------------
+// World box / radius range.  out[0..2] = min xyz, out[3..5] = max xyz, out[6] = min radius, out[7] = max radius, all in
+// the order preserving uint encoding (initialise mins with 0xffffffff and maxs with 0).
+// For double input the (float) cast of the reference (TreeNSearch.cpp:275-296) happens here and the converted arrays are
+// written out so that every later kernel only sees float.
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<double>(double v) { return __double2float_rn(v); }
+
+constexpr int kAabbThreads = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kAabbThreads) aabb_kernel(const T* __restrict__ pts, const T* __restrict__ radii, int n,
+                                                            float* __restrict__ pts_f32_out, float* __restrict__ radii_f32_out,
+                                                            uint32_t* __restrict__ out)
+{
+    float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    float rlo = INFINITY, rhi = -INFINITY;
+    // flat walk over the 3n coordinates: fully coalesced, component = flat index mod 3
+    const int64_t total = 3ll * n;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 3;
+    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 3; base < total; base += stride) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float v = to_f32<T>(pts[base + c]);
+            if (pts_f32_out) pts_f32_out[base + c] = v;
+            lo[c] = fminf(lo[c], v);
+            hi[c] = fmaxf(hi[c], v);
+        }
+    }
+    if (radii) {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const float r = to_f32<T>(radii[i]);
+            if (radii_f32_out) radii_f32_out[i] = r;
+            rlo = fminf(rlo, r);
+            rhi = fmaxf(rhi, r);
+        }
+    }
+    uint32_t v[8] = { float_to_ordered(lo[0]), float_to_ordered(lo[1]), float_to_ordered(lo[2]),
+                      float_to_ordered(hi[0]), float_to_ordered(hi[1]), float_to_ordered(hi[2]),
+                      float_to_ordered(rlo), float_to_ordered(rhi) };
+    __shared__ uint32_t s_red[8][kAabbThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const bool is_min = (k < 3) || (k == 6);
+        const uint32_t r = is_min ? __reduce_min_sync(kFull, v[k]) : __reduce_max_sync(kFull, v[k]);
+        if (lane == 0) s_red[k][warp] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        const int k = threadIdx.x;
+        const bool is_min = (k < 3) || (k == 6);
+        uint32_t r = s_red[k][0];
+        for (int w = 1; w < kAabbThreads / 32; w++) r = is_min ? min(r, s_red[k][w]) : max(r, s_red[k][w]);
+        if (k < 6 || radii) {
+            if (is_min) atomicMin(&out[k], r); else atomicMax(&out[k], r);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// Cell assignment + Morton key.  ijk = floor((p - bottom) * inv_cell) like TreeNSearch.cpp:713-715, but in fp64 and clamped.
+template <typename Key>
+__global__ void __launch_bounds__(256) keygen_kernel(const float* __restrict__ pts, int n, GridParams g, Key* __restrict__ keys)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = pts[3ll * i], y = pts[3ll * i + 1], z = pts[3ll * i + 2];
+    int cx = __double2int_rd(((double)x - g.bottom[0]) * g.inv_cell);
+    int cy = __double2int_rd(((double)y - g.bottom[1]) * g.inv_cell);
+    int cz = __double2int_rd(((double)z - g.bottom[2]) * g.inv_cell);
+    cx = min(max(cx, 0), g.max_coord);
+    cy = min(max(cy, 0), g.max_coord);
+    cz = min(max(cz, 0), g.max_coord);
+    keys[i] = Morton<Key>::encode((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// Reorder: sorted[i] = (x, y, z, bits(idx)) of the point that the sort put at position i; r2[i] = r*r (float, like
+// TreeNSearch.cpp:2352) in variable radius mode.  ids[] (optional) replaces the set-local index by a caller supplied id.
+__global__ void __launch_bounds__(256) reorder_kernel(const float* __restrict__ pts, const float* __restrict__ radii, const uint32_t* __restrict__ order,
+                                                      int n, float4* __restrict__ sorted, float* __restrict__ sorted_r2)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t src = order[i];
+    const float* p = pts + 3ll * src;
+    sorted[i] = make_float4(p[0], p[1], p[2], __uint_as_float(src));
+    if (radii) {
+        const float r = radii[src];
+        sorted_r2[i] = __fmul_rn(r, r);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// Cell start/end compaction over the sorted keys + open addressing hash (cell key -> compact cell id).
+constexpr int kCellThreads = 256;
+constexpr int kCellItems = 4;
+constexpr int kCellTile = kCellThreads * kCellItems;
+
+__device__ __forceinline__ uint32_t cas_key(uint32_t* a, uint32_t expected, uint32_t v) { return atomicCAS(a, expected, v); }
+__device__ __forceinline__ uint64_t cas_key(uint64_t* a, uint64_t expected, uint64_t v)
+{
+    return (uint64_t)atomicCAS(reinterpret_cast<unsigned long long*>(a), (unsigned long long)expected, (unsigned long long)v);
+}
+
+template <typename Key>
+__global__ void __launch_bounds__(kCellThreads) count_heads_kernel(const Key* __restrict__ keys, int n, uint32_t* __restrict__ tile_heads)
+{
+    __shared__ uint32_t warp_sums[8];
+    const int base = blockIdx.x * kCellTile + threadIdx.x * kCellItems;
+    uint32_t c = 0;
+    Key prev = (base > 0 && base - 1 < n) ? keys[base - 1] : (Key)0;
+#pragma unroll
+    for (int i = 0; i < kCellItems; i++) {
+        const int idx = base + i;
+        if (idx < n) {
+            const Key k = keys[idx];
+            c += (idx == 0 || k != prev) ? 1u : 0u;
+            prev = k;
+        }
+    }
+    uint32_t total;
+    block_exclusive_scan_256(c, warp_sums, total);
+    if (threadIdx.x == 0) tile_heads[blockIdx.x] = total;
+}
+
+template <typename Key>
+__global__ void __launch_bounds__(kCellThreads) emit_cells_kernel(const Key* __restrict__ keys, int n, const uint32_t* __restrict__ tile_base,
+                                                                  Key* __restrict__ cell_key, uint32_t* __restrict__ cell_start,
+                                                                  Key* __restrict__ hkeys, uint32_t* __restrict__ hvals, int hash_log2)
+{
+    __shared__ uint32_t warp_sums[8];
+    const int base = blockIdx.x * kCellTile + threadIdx.x * kCellItems;
+    Key k[kCellItems];
+    bool head[kCellItems];
+    uint32_t c = 0;
+    Key prev = (base > 0 && base - 1 < n) ? keys[base - 1] : (Key)0;
+#pragma unroll
+    for (int i = 0; i < kCellItems; i++) {
+        const int idx = base + i;
+        head[i] = false;
+        k[i] = (Key)0;
+        if (idx < n) {
+            k[i] = keys[idx];
+            head[i] = (idx == 0 || k[i] != prev);
+            prev = k[i];
+            c += head[i] ? 1u : 0u;
+        }
+    }
+    uint32_t total;
+    uint32_t cid = block_exclusive_scan_256(c, warp_sums, total) + tile_base[blockIdx.x];
+    const uint32_t hmask = (1u << hash_log2) - 1u;
+#pragma unroll
+    for (int i = 0; i < kCellItems; i++) {
+        if (head[i]) {
+            cell_key[cid] = k[i];
+            cell_start[cid] = (uint32_t)(base + i);
+            uint32_t slot = Morton<Key>::hash(k[i]) >> (32 - hash_log2);
+            for (;;) {
+                const Key old = cas_key(&hkeys[slot], Morton<Key>::kEmpty, k[i]);
+                if (old == Morton<Key>::kEmpty) { hvals[slot] = cid; break; }
+                slot = (slot + 1) & hmask;
+            }
+            cid++;
+        }
+    }
+    // sentinel: cell_start[n_cells] = n
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kCellThreads - 1) cell_start[cid] = (uint32_t)n;
+}
+
+// gather used by tnsb_apply_zsort_device_f32
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, const int32_t* __restrict__ new_to_old,
+                                                          int n, int stride)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n * stride) return;
+    const int row = (int)(t / stride), c = (int)(t % stride);
+    dst[t] = src[(int64_t)new_to_old[row] * stride + c];
+}
+
+}  // namespace tnsb

@@ -1,0 +1,397 @@
+// query.cuh -- the 27-cell fixed-radius distance query.  Replaces _solve_leaves / _prepare_brute_force[_simd] /
+// _brute_force[_simd] of the reference (TreeNSearch.cpp:1823-1872, :2161-2399, :2400-2569).
+//
+// Work decomposition (one launch per active ordered pair set_i -> set_j):
+//   * a task is one occupied cell of set_i; a warp pulls batches of consecutive (Morton ordered) cells from a ticket counter;
+//   * lanes 0..26 look the 27 neighbour cells of set_j up in the cell hash and a warp scan turns their populations into a
+//     dense candidate list; every lane then owns candidate t = slot*32 + lane and keeps it in REGISTERS for the whole cell
+//     (one coalesced 16-byte load per candidate per cell, instead of one per (query, candidate) pair);
+//   * for each query point of the cell (broadcast with shuffles) every lane tests its candidates with the reference's exact
+//     arithmetic  d2 = fma(dz,dz, fma(dx,dx, dy*dy)) <= r^2  (TreeNSearch.cpp:2477-2486 as compiled),
+//     a warp scan of the per-lane hit counts gives the list size and every lane's slot, hits are compacted into a per-warp
+//     shared-memory staging buffer as  [n, j0, j1, ...]  (the reference's list layout, TreeNSearch.h:395);
+//   * when the staging buffer is full the warp reserves a range of the global ragged buffer with ONE atomicAdd, copies the
+//     staged lists with fully coalesced stores and publishes list_pos[i] for the staged queries.
+// Lists are therefore written exactly once, in one pass (no count pass), and nothing is ever re-read from HBM.
+//
+// Self exclusion: only the identical (set, index) is excluded (TreeNSearch.cpp:2464-2466); coincident points are neighbours.
+#pragma once
+#include "common.cuh"
+
+namespace tnsb {
+
+constexpr int kQueryThreads = 256;
+constexpr int kQueryWarps = kQueryThreads / 32;
+constexpr int kStageInts = 2048;          // per-warp staging capacity (ints)
+constexpr int kStageRecs = 256;           // per-warp staged list records
+constexpr int kCellsPerTicket = 8;
+constexpr int kWarpSmemInts = kStageInts + 2 * kStageRecs + 64;
+constexpr int kQuerySmemBytes = kQueryWarps * kWarpSmemInts * 4;
+
+template <typename Key>
+struct QueryArgs {
+    // searching set (set_i)
+    const float4* q_pts;          // sorted (x, y, z, bits(index))
+    const float* q_r2;            // sorted r^2 (variable radius mode)
+    const Key* q_cell_key;
+    const uint32_t* q_cell_start; // n_q_cells + 1
+    int n_q_cells;
+    int query_limit;              // points with index >= limit are find-only (INT_MAX: none)
+    // searched set (set_j)
+    const float4* c_pts;
+    const float* c_r2;
+    const uint32_t* c_cell_start;
+    const Key* hkeys;
+    const uint32_t* hvals;
+    int hash_log2;
+    int same_set;
+    int max_coord;
+    float r2_fixed;
+    // output
+    int32_t* ragged;
+    long long capacity;
+    long long* list_pos;
+    unsigned long long* cursor;   // next free int of the ragged buffer
+    uint32_t* ticket;
+    unsigned long long* n_neighbors;
+    int* nb_min;
+    int* nb_max;
+    int* overflow;
+};
+
+struct WarpStage {
+    int* ints;       // [kStageInts]
+    int* rec_idx;    // [kStageRecs]
+    int* rec_off;    // [kStageRecs]
+    int* run_start;  // [32]
+    int* run_pre;    // [32]
+    int wpos;
+    int nrec;
+};
+
+template <typename Key>
+__device__ __forceinline__ void stage_flush(WarpStage& st, const QueryArgs<Key>& a, int lane)
+{
+    __syncwarp();
+    if (st.wpos > 0) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.cursor, (unsigned long long)st.wpos);
+        base = __shfl_sync(kFull, base, 0);
+        if ((long long)(base + st.wpos) <= a.capacity) {
+            for (int t = lane; t < st.wpos; t += 32) a.ragged[base + t] = st.ints[t];
+            for (int k = lane; k < st.nrec; k += 32) a.list_pos[st.rec_idx[k]] = (long long)base + st.rec_off[k];
+        } else if (lane == 0) {
+            *a.overflow = 1;
+        }
+    }
+    st.wpos = 0;
+    st.nrec = 0;
+    __syncwarp();
+}
+
+// reserve room for one list of n ids.  Returns the destination of the count word: either inside the staging buffer
+// (global == false) or, for lists that do not fit the staging buffer at all, directly in the ragged buffer.
+template <typename Key>
+__device__ __forceinline__ int* reserve_list(WarpStage& st, const QueryArgs<Key>& a, int lane, int qidx, int n, bool& ok)
+{
+    ok = true;
+    if (n + 1 > kStageInts) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.cursor, (unsigned long long)(n + 1));
+        base = __shfl_sync(kFull, base, 0);
+        if ((long long)(base + n + 1) > a.capacity) {
+            if (lane == 0) *a.overflow = 1;
+            ok = false;
+            return nullptr;
+        }
+        if (lane == 0) {
+            a.ragged[base] = n;
+            a.list_pos[qidx] = (long long)base;
+        }
+        return a.ragged + base;
+    }
+    if (st.wpos + n + 1 > kStageInts || st.nrec == kStageRecs) stage_flush(st, a, lane);
+    int* dst = st.ints + st.wpos;
+    if (lane == 0) {
+        dst[0] = n;
+        st.rec_idx[st.nrec] = qidx;
+        st.rec_off[st.nrec] = st.wpos;
+    }
+    st.wpos += n + 1;
+    st.nrec += 1;
+    return dst;
+}
+
+__device__ __forceinline__ int warp_inclusive_scan(int v, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// the reference's distance, with explicit roundings (the library is also built with -fmad=false)
+__device__ __forceinline__ float dist2(float qx, float qy, float qz, float cx, float cy, float cz)
+{
+    const float dx = __fsub_rn(qx, cx);
+    const float dy = __fsub_rn(qy, cy);
+    const float dz = __fsub_rn(qz, cz);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+// candidate t of the dense list -> position in the sorted array of set_j (5-step search of the 32-entry run table)
+__device__ __forceinline__ int candidate_pos(const WarpStage& st, int t)
+{
+    int rho = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1)
+        if (st.run_pre[rho + step] <= t) rho += step;
+    return st.run_start[rho] + (t - st.run_pre[rho]);
+}
+
+template <typename Key, int NSLOT, bool VARIABLE, bool SYMMETRIC>
+__global__ void __launch_bounds__(kQueryThreads, 2) query_kernel(const QueryArgs<Key> a)
+{
+    extern __shared__ int s_mem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpStage st;
+    st.ints = s_mem + warp * kWarpSmemInts;
+    st.rec_idx = st.ints + kStageInts;
+    st.rec_off = st.rec_idx + kStageRecs;
+    st.run_start = st.rec_off + kStageRecs;
+    st.run_pre = st.run_start + 32;
+    st.wpos = 0;
+    st.nrec = 0;
+
+    // neighbour cell offset owned by this lane (lanes 27..31 idle during the lookup)
+    const int ox = lane % 3 - 1, oy = (lane / 3) % 3 - 1, oz = lane / 9 - 1;
+    const uint32_t hmask = (1u << a.hash_log2) - 1u;
+
+    unsigned long long nb_sum = 0;
+    int nb_lo = 0x7fffffff, nb_hi = 0;
+
+    for (;;) {
+        uint32_t c0 = 0;
+        if (lane == 0) c0 = atomicAdd(a.ticket, (uint32_t)kCellsPerTicket);
+        c0 = __shfl_sync(kFull, c0, 0);
+        if (c0 >= (uint32_t)a.n_q_cells) break;
+        const uint32_t c1 = min(c0 + (uint32_t)kCellsPerTicket, (uint32_t)a.n_q_cells);
+
+        for (uint32_t c = c0; c < c1; c++) {
+            // ---------------- the 27 neighbour runs of this cell
+            const Key key = a.q_cell_key[c];
+            const int qb = (int)a.q_cell_start[c], qe = (int)a.q_cell_start[c + 1];
+            int cx, cy, cz;
+            Morton<Key>::decode(key, cx, cy, cz);
+            int rs = 0, rc = 0;
+            {
+                const int nx = cx + ox, ny = cy + oy, nz = cz + oz;
+                if (lane < 27 && nx >= 0 && ny >= 0 && nz >= 0 && nx <= a.max_coord && ny <= a.max_coord && nz <= a.max_coord) {
+                    const Key nkey = Morton<Key>::encode((uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
+                    uint32_t slot = Morton<Key>::hash(nkey) >> (32 - a.hash_log2);
+                    for (;;) {
+                        const Key k = a.hkeys[slot];
+                        if (k == nkey) {
+                            const uint32_t cid = a.hvals[slot];
+                            rs = (int)a.c_cell_start[cid];
+                            rc = (int)a.c_cell_start[cid + 1] - rs;
+                            break;
+                        }
+                        if (k == Morton<Key>::kEmpty) break;
+                        slot = (slot + 1) & hmask;
+                    }
+                }
+            }
+            const int inc = warp_inclusive_scan(rc, lane);
+            const int T = __shfl_sync(kFull, inc, 31);
+            __syncwarp();
+            st.run_start[lane] = rs;
+            st.run_pre[lane] = inc - rc;
+            __syncwarp();
+            const int self_pre = a.same_set ? st.run_pre[13] : 0;   // lane 13 = offset (0,0,0)
+
+            if (T <= NSLOT * 32) {
+                // ---------------- fast path: the whole candidate list lives in registers
+                float px[NSLOT], py[NSLOT], pz[NSLOT];
+                int pid[NSLOT];
+                float pr2[SYMMETRIC ? NSLOT : 1];
+#pragma unroll
+                for (int s = 0; s < NSLOT; s++) {
+                    px[s] = 3.0e38f; py[s] = 0.0f; pz[s] = 0.0f; pid[s] = -1;
+                    if (SYMMETRIC) pr2[s] = -1.0f;
+                    if (s * 32 < T) {
+                        const int t = s * 32 + lane;
+                        if (t < T) {
+                            const int pos = candidate_pos(st, t);
+                            const float4 v = a.c_pts[pos];
+                            px[s] = v.x; py[s] = v.y; pz[s] = v.z; pid[s] = __float_as_int(v.w);
+                            if (SYMMETRIC) pr2[s] = a.c_r2[pos];
+                        }
+                    }
+                }
+                for (int q0 = qb; q0 < qe; q0 += 32) {
+                    const int qi = q0 + lane;
+                    float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float qr2 = a.r2_fixed;
+                    if (qi < qe) {
+                        qv = a.q_pts[qi];
+                        if (VARIABLE) qr2 = a.q_r2[qi];
+                    }
+                    const int nq = min(32, qe - q0);
+                    for (int k = 0; k < nq; k++) {
+                        const int qidx = __float_as_int(__shfl_sync(kFull, qv.w, k));
+                        if (qidx >= a.query_limit) continue;
+                        const float qx = __shfl_sync(kFull, qv.x, k);
+                        const float qy = __shfl_sync(kFull, qv.y, k);
+                        const float qz = __shfl_sync(kFull, qv.z, k);
+                        const float r2 = VARIABLE ? __shfl_sync(kFull, qr2, k) : a.r2_fixed;
+                        uint32_t hits = 0;
+#pragma unroll
+                        for (int s = 0; s < NSLOT; s++) {
+                            if (s * 32 < T) {
+                                const float d2 = dist2(qx, qy, qz, px[s], py[s], pz[s]);
+                                bool h = d2 <= r2;
+                                if (SYMMETRIC) h = h || (d2 <= pr2[s]);
+                                hits |= (h ? 1u : 0u) << s;
+                            }
+                        }
+                        if (a.same_set) {
+                            const int ts = self_pre + (q0 + k - qb);
+                            if (lane == (ts & 31)) hits &= ~(1u << (ts >> 5));
+                        }
+                        const int cnt = __popc(hits);
+                        const int cinc = warp_inclusive_scan(cnt, lane);
+                        const int n = __shfl_sync(kFull, cinc, 31);
+                        nb_sum += (unsigned long long)n;
+                        nb_lo = min(nb_lo, n);
+                        nb_hi = max(nb_hi, n);
+                        bool ok;
+                        int* dst = reserve_list(st, a, lane, qidx, n, ok);
+                        if (ok) {
+                            int p = 1 + cinc - cnt;
+#pragma unroll
+                            for (int s = 0; s < NSLOT; s++) {
+                                if (s * 32 < T) {
+                                    if (hits & (1u << s)) dst[p++] = pid[s];
+                                }
+                            }
+                        }
+                    }
+                }
+            } else {
+                // ---------------- general path (very dense neighbourhoods): two sweeps per query, candidates re-read through L1
+                for (int qi = qb; qi < qe; qi++) {
+                    const float4 qv = a.q_pts[qi];
+                    const int qidx = __float_as_int(qv.w);
+                    if (qidx >= a.query_limit) continue;
+                    const float r2 = VARIABLE ? a.q_r2[qi] : a.r2_fixed;
+                    const int ts = a.same_set ? self_pre + (qi - qb) : -1;
+                    int n = 0;
+                    for (int t0 = 0; t0 < T; t0 += 32) {
+                        const int t = t0 + lane;
+                        bool h = false;
+                        if (t < T && t != ts) {
+                            const int pos = candidate_pos(st, t);
+                            const float4 v = a.c_pts[pos];
+                            const float d2 = dist2(qv.x, qv.y, qv.z, v.x, v.y, v.z);
+                            h = d2 <= r2;
+                            if (SYMMETRIC) h = h || (d2 <= a.c_r2[pos]);
+                        }
+                        n += __popc(__ballot_sync(kFull, h));
+                    }
+                    nb_sum += (unsigned long long)n;
+                    nb_lo = min(nb_lo, n);
+                    nb_hi = max(nb_hi, n);
+                    bool ok;
+                    int* dst = reserve_list(st, a, lane, qidx, n, ok);
+                    if (!ok) continue;
+                    int p = 1;
+                    const unsigned lt = lanemask_lt();
+                    for (int t0 = 0; t0 < T; t0 += 32) {
+                        const int t = t0 + lane;
+                        bool h = false;
+                        int id = -1;
+                        if (t < T && t != ts) {
+                            const int pos = candidate_pos(st, t);
+                            const float4 v = a.c_pts[pos];
+                            const float d2 = dist2(qv.x, qv.y, qv.z, v.x, v.y, v.z);
+                            h = d2 <= r2;
+                            if (SYMMETRIC) h = h || (d2 <= a.c_r2[pos]);
+                            id = __float_as_int(v.w);
+                        }
+                        const unsigned m = __ballot_sync(kFull, h);
+                        if (h) dst[p + __popc(m & lt)] = id;
+                        p += __popc(m);
+                    }
+                }
+            }
+        }
+    }
+    stage_flush(st, a, lane);
+    if (lane == 0) {
+        if (nb_sum) atomicAdd(a.n_neighbors, nb_sum);
+        if (nb_lo != 0x7fffffff) atomicMin(a.nb_min, nb_lo);
+        atomicMax(a.nb_max, nb_hi);
+    }
+}
+
+// ---- optional post pass: sort every list ascending (one warp per list, bitonic in registers for n <= 32*kSortPerLane) ----
+constexpr int kListSortPerLane = 4;    // lists up to 128 ids are sorted in registers, longer ones by an in-place odd-even pass
+
+__global__ void __launch_bounds__(256) sort_lists_kernel(int32_t* __restrict__ ragged, const long long* __restrict__ list_pos, int n_lists, int query_limit)
+{
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_lists || w >= query_limit) return;
+    int32_t* l = ragged + list_pos[w];
+    const int n = l[0];
+    l += 1;
+    if (n <= 1) return;
+    if (n <= 32 * kListSortPerLane) {
+        // bitonic sort over 128 virtual elements: element e lives in lane (e & 31), register (e >> 5)
+        int v[kListSortPerLane];
+#pragma unroll
+        for (int r = 0; r < kListSortPerLane; r++) {
+            const int e = r * 32 + lane;
+            v[r] = e < n ? l[e] : 0x7fffffff;
+        }
+#pragma unroll
+        for (int k = 2; k <= 32 * kListSortPerLane; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j >= 1; j >>= 1) {
+                int o[kListSortPerLane];
+#pragma unroll
+                for (int r = 0; r < kListSortPerLane; r++) o[r] = v[r];
+#pragma unroll
+                for (int r = 0; r < kListSortPerLane; r++) {
+                    const int e = r * 32 + lane;
+                    int other;
+                    if (j >= 32) other = o[r ^ (j >> 5)];
+                    else other = __shfl_xor_sync(kFull, o[r], j);
+                    const bool up = (e & k) == 0;
+                    const bool lower = (e & j) == 0;
+                    const int lo = min(o[r], other), hi = max(o[r], other);
+                    v[r] = (lower == up) ? lo : hi;
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kListSortPerLane; r++) {
+            const int e = r * 32 + lane;
+            if (e < n) l[e] = v[r];
+        }
+    } else {
+        // odd-even transposition in global/L2 memory (rare: > 128 neighbours)
+        for (int pass = 0; pass < n; pass++) {
+            for (int e = (pass & 1) + 2 * lane; e + 1 < n; e += 64) {
+                const int x = l[e], y = l[e + 1];
+                if (x > y) { l[e] = y; l[e + 1] = x; }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+}  // namespace tnsb

@@ -1,0 +1,972 @@
+// tnsb.cu -- context, host orchestration and the C ABI (include/tnsb.h) of the B200 neighbour-search engine.
+//
+// Host-side mirror of the reference's driver layer: set bookkeeping and validation (TreeNSearch.cpp:20-261, :263-392),
+// and run() (TreeNSearch.cpp:138-149) re-expressed as a sequence of CUDA stages on one stream:
+//     upload -> world box -> Morton keys -> radix sort -> reorder -> cell start/end + hash -> 27-cell query -> host mirror
+// There is deliberately no CPU fallback: every entry point fails with TNSB_ERR_NO_DEVICE / TNSB_ERR_CUDA when CUDA is unusable.
+#include "../../include/tnsb.h"
+
+#include "common.cuh"
+#include "scan.cuh"
+#include "radix_sort.cuh"
+#include "grid_build.cuh"
+#include "query.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace tnsb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes, double headroom = 1.0)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        const size_t want = (size_t)((double)bytes * headroom) + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess && headroom > 1.0) { cudaGetLastError(); e = cudaMalloc(&p, bytes + 256); if (e == cudaSuccess) { cap = bytes + 256; return e; } }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes, double headroom = 1.0)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        const size_t want = (size_t)((double)bytes * headroom) + 256;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PairCounters {
+    unsigned long long cursor;
+    unsigned long long n_neighbors;
+    uint32_t ticket;
+    int nb_min;
+    int nb_max;
+    int overflow;
+};
+
+struct SetState {
+    // borrowed user arrays (TreeNSearch.cpp:35-66): exactly one of f32 / f64 is used
+    const float* u_pts_f32 = nullptr;
+    const float* u_radii_f32 = nullptr;
+    const double* u_pts_f64 = nullptr;
+    const double* u_radii_f64 = nullptr;
+    bool is_f64 = false;
+    bool has_radii = false;
+    int n = 0;
+    // device state
+    DevBuf up_pts, up_radii;       // uploaded raw arrays (when the user arrays live on the host)
+    DevBuf cv_pts, cv_radii;       // float conversions of double arrays
+    const float* d_pts = nullptr;  // float xyz actually used by the kernels
+    const float* d_radii = nullptr;
+    DevBuf keys[2], vals[2];
+    int sel = 0;
+    DevBuf sorted, sorted_r2;
+    DevBuf cell_key, cell_start, tile_heads;
+    DevBuf hkeys, hvals;
+    int hash_log2 = 1;
+    int n_cells = 0;
+    bool sorted_valid = false;     // "are_cells_valid" of the reference (TreeNSearch.cpp:148)
+    // zsort
+    std::vector<int32_t> zsort_new_to_old;
+    DevBuf d_zorder;
+    bool zorder_ready = false;
+};
+
+struct PairState {
+    DevBuf d_ragged, d_list_pos;
+    PinBuf h_ragged, h_list_pos;
+    int64_t capacity = 0;      // ints
+    int64_t n_ints = 0;
+    int64_t n_neighbors = 0;
+    int nb_min = 0, nb_max = 0;
+    int n_lists = 0;
+    bool valid = false;
+    bool host_valid = false;
+};
+
+enum Stage { EV_BEGIN = 0, EV_UPLOAD, EV_AABB, EV_KEYS, EV_SORT, EV_REORDER, EV_CELLS, EV_QUERY, EV_DOWNLOAD, EV_COUNT };
+
+}  // namespace
+
+struct tnsb_context {
+    int device = 0;
+    int n_sms = 148;
+    cudaStream_t stream = nullptr;       // stream in use
+    cudaStream_t own_stream = nullptr;   // created by tnsb_create
+    cudaEvent_t ev[EV_COUNT] = {};
+    std::string err;
+
+    std::vector<SetState> sets;
+    std::vector<std::vector<uint8_t>> active;     // [set_i][set_j], default false (TreeNSearch.cpp:357-361)
+    int n_sets_with_radii = 0;                    // set_radii.size() of the reference
+    bool radius_set = false;
+    float radius = -1.0f, radius_sq = -1.0f;
+    bool symmetric = true;                        // TreeNSearch.h:385
+    float user_cell_size = -1.0f;
+
+    // options
+    bool opt_host_results = true;
+    bool opt_pin_user = false;
+    int64_t opt_list_capacity = 48;
+    int64_t opt_query_limit = -1;
+    bool opt_sort_lists = false;
+
+    // world box with hysteresis (TreeNSearch.cpp:474-482)
+    bool domain_valid = false;
+    double dom_bottom[3] = { 0, 0, 0 }, dom_top[3] = { 0, 0, 0 };
+    double cell = 0.0;
+    int bits = 0;
+    bool key64 = false;
+
+    DevBuf d_reduce;        // 8 x uint32
+    DevBuf d_counters;      // PairCounters per pair
+    DevBuf d_misc;          // n_cells per set (uint32)
+    DevBuf sort_temp, scan_temp;
+    PinBuf h_small;         // reduce results, counters, n_cells
+    std::vector<PairState> pairs;
+    std::map<const void*, size_t> registered;
+    tnsb_stats stats;
+
+    tnsb_context() { memset(&stats, 0, sizeof(stats)); }
+};
+
+namespace {
+
+int fail(tnsb_context* c, int code, const std::string& msg)
+{
+    if (c) c->err = msg;
+    return code;
+}
+
+#define TNSB_CUDA(c, call)                                                                                   \
+    do {                                                                                                     \
+        cudaError_t e__ = (call);                                                                            \
+        if (e__ != cudaSuccess) {                                                                            \
+            cudaGetLastError();                                                                              \
+            return fail((c), TNSB_ERR_CUDA, std::string("CUDA error in " #call ": ") + cudaGetErrorString(e__)); \
+        }                                                                                                    \
+    } while (0)
+
+bool is_device_pointer(const void* p)
+{
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+bool is_pinned_pointer(const void* p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// makes `src` (host or device) available on the device; returns the device pointer in *out
+int stage_input(tnsb_context* c, const void* src, size_t bytes, DevBuf& up, const void** out)
+{
+    if (bytes == 0 || !src) { *out = nullptr; return TNSB_OK; }
+    if (is_device_pointer(src)) { *out = src; return TNSB_OK; }
+    TNSB_CUDA(c, up.ensure(bytes, 1.1));
+    if (c->opt_pin_user && !is_pinned_pointer(src)) {
+        auto it = c->registered.find(src);
+        if (it == c->registered.end() || it->second < bytes) {
+            if (it != c->registered.end()) { cudaHostUnregister(const_cast<void*>(src)); c->registered.erase(it); }
+            if (cudaHostRegister(const_cast<void*>(src), bytes, cudaHostRegisterDefault) == cudaSuccess) c->registered[src] = bytes;
+            else cudaGetLastError();   // fall back to a pageable copy
+        }
+    }
+    TNSB_CUDA(c, cudaMemcpyAsync(up.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    c->stats.h2d_bytes += (int64_t)bytes;
+    *out = up.p;
+    return TNSB_OK;
+}
+
+int validate(tnsb_context* c)
+{
+    // TreeNSearch::_check(), TreeNSearch.cpp:366-392
+    if (c->radius_set && c->radius <= 0.0f) return fail(c, TNSB_ERR_INVALID_STATE, "TreeNSearch error: global_search_radius <= 0.");
+    if (c->radius_set && c->n_sets_with_radii > 0)
+        return fail(c, TNSB_ERR_INVALID_STATE, "TreeNSearch error: global search radius and per-point variable search radii specified.");
+    if (!c->radius_set && c->n_sets_with_radii != (int)c->sets.size())
+        return fail(c, TNSB_ERR_INVALID_STATE, "TreeNSearch error: not all point sets have per-point search radius specified.");
+    return TNSB_OK;
+}
+
+template <typename Key>
+int build_sets(tnsb_context* c, const GridParams& gp)
+{
+    cudaStream_t s = c->stream;
+    int& launches = c->stats.n_kernel_launches;
+    const int key_bits = 3 * gp.bits;
+    // ---- cell assignment + Morton keys
+    for (auto& st : c->sets) {
+        if (st.n == 0) continue;
+        for (int b = 0; b < 2; b++) {
+            TNSB_CUDA(c, st.keys[b].ensure(sizeof(Key) * (size_t)st.n, 1.1));
+            TNSB_CUDA(c, st.vals[b].ensure(sizeof(uint32_t) * (size_t)st.n, 1.1));
+        }
+        keygen_kernel<Key><<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.n, gp, st.keys[0].as<Key>());
+        launches++;
+    }
+    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_KEYS], s));
+    // ---- radix sort of (key, index)
+    for (auto& st : c->sets) {
+        if (st.n == 0) continue;
+        TNSB_CUDA(c, c->sort_temp.ensure(sizeof(uint32_t) * (size_t)radix_sort_temp_elems<Key>(st.n), 1.1));
+        Key* keys[2] = { st.keys[0].as<Key>(), st.keys[1].as<Key>() };
+        uint32_t* vals[2] = { st.vals[0].as<uint32_t>(), st.vals[1].as<uint32_t>() };
+        int passes = 0;
+        st.sel = radix_sort_pairs<Key>(keys, vals, st.n, key_bits, c->sort_temp.as<uint32_t>(), s, &launches, &passes);
+        c->stats.sort_passes = std::max(c->stats.sort_passes, passes);
+    }
+    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_SORT], s));
+    // ---- reorder
+    for (auto& st : c->sets) {
+        if (st.n == 0) continue;
+        TNSB_CUDA(c, st.sorted.ensure(sizeof(float4) * (size_t)st.n, 1.1));
+        if (st.has_radii) TNSB_CUDA(c, st.sorted_r2.ensure(sizeof(float) * (size_t)st.n, 1.1));
+        reorder_kernel<<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.has_radii ? st.d_radii : nullptr, st.vals[st.sel].as<uint32_t>(), st.n,
+                                                          st.sorted.as<float4>(), st.sorted_r2.as<float>());
+        launches++;
+    }
+    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_REORDER], s));
+    // ---- cell heads: count, scan, (one sync for the cell counts), emit + hash
+    const int n_sets = (int)c->sets.size();
+    TNSB_CUDA(c, c->d_misc.ensure(sizeof(uint32_t) * (size_t)std::max(n_sets, 1)));
+    for (int si = 0; si < n_sets; si++) {
+        auto& st = c->sets[si];
+        st.n_cells = 0;
+        if (st.n == 0) continue;
+        const int n_tiles = ceil_div(st.n, kCellTile);
+        TNSB_CUDA(c, st.tile_heads.ensure(sizeof(uint32_t) * ((size_t)n_tiles + exclusive_scan_temp_elems(n_tiles)), 1.1));
+        uint32_t* th = st.tile_heads.as<uint32_t>();
+        count_heads_kernel<Key><<<n_tiles, kCellThreads, 0, s>>>(st.keys[st.sel].as<Key>(), st.n, th);
+        launches += 1 + exclusive_scan_u32(th, th, n_tiles, th + n_tiles, c->d_misc.as<uint32_t>() + si, s);
+    }
+    uint32_t* h_ncells = c->h_small.as<uint32_t>() + 64;
+    TNSB_CUDA(c, cudaMemcpyAsync(h_ncells, c->d_misc.p, sizeof(uint32_t) * (size_t)std::max(n_sets, 1), cudaMemcpyDeviceToHost, s));
+    TNSB_CUDA(c, cudaStreamSynchronize(s));
+    for (int si = 0; si < n_sets; si++) {
+        auto& st = c->sets[si];
+        // hash table sized to <= 50% load; always at least 2 slots so that lookups into an empty set terminate
+        st.n_cells = st.n > 0 ? (int)h_ncells[si] : 0;
+        int lg = 1;
+        while ((1ll << lg) < 2ll * st.n_cells) lg++;
+        st.hash_log2 = lg;
+        const size_t hs = (size_t)1 << lg;
+        TNSB_CUDA(c, st.hkeys.ensure(sizeof(Key) * hs, 1.25));
+        TNSB_CUDA(c, st.hvals.ensure(sizeof(uint32_t) * hs, 1.25));
+        TNSB_CUDA(c, cudaMemsetAsync(st.hkeys.p, 0xff, sizeof(Key) * hs, s));
+        c->stats.n_cells += st.n_cells;
+        if (st.n == 0) continue;
+        TNSB_CUDA(c, st.cell_key.ensure(sizeof(Key) * ((size_t)st.n_cells + 1), 1.25));
+        TNSB_CUDA(c, st.cell_start.ensure(sizeof(uint32_t) * ((size_t)st.n_cells + 2), 1.25));
+        const int n_tiles = ceil_div(st.n, kCellTile);
+        emit_cells_kernel<Key><<<n_tiles, kCellThreads, 0, s>>>(st.keys[st.sel].as<Key>(), st.n, st.tile_heads.as<uint32_t>(), st.cell_key.as<Key>(),
+                                                              st.cell_start.as<uint32_t>(), st.hkeys.as<Key>(), st.hvals.as<uint32_t>(), st.hash_log2);
+        launches++;
+        st.sorted_valid = true;
+    }
+    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_CELLS], s));
+    TNSB_CUDA(c, cudaGetLastError());
+    return TNSB_OK;
+}
+
+template <typename Key, int NSLOT>
+cudaError_t launch_query(const QueryArgs<Key>& a, bool variable, bool symmetric, int grid, cudaStream_t s)
+{
+    auto go = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQuerySmemBytes);
+        if (e != cudaSuccess) return e;
+        kernel<<<grid, kQueryThreads, kQuerySmemBytes, s>>>(a);
+        return cudaGetLastError();
+    };
+    if (!variable) return go(query_kernel<Key, NSLOT, false, false>);
+    if (!symmetric) return go(query_kernel<Key, NSLOT, true, false>);
+    return go(query_kernel<Key, NSLOT, true, true>);
+}
+
+template <typename Key>
+int query_pair(tnsb_context* c, int si, int sj, const GridParams& gp, PairCounters* d_cnt)
+{
+    auto& qi = c->sets[si];
+    auto& cj = c->sets[sj];
+    PairState& ps = c->pairs[si * c->sets.size() + sj];
+    QueryArgs<Key> a;
+    a.q_pts = qi.sorted.as<float4>();
+    a.q_r2 = qi.sorted_r2.as<float>();
+    a.q_cell_key = qi.cell_key.as<Key>();
+    a.q_cell_start = qi.cell_start.as<uint32_t>();
+    a.n_q_cells = qi.n_cells;
+    a.query_limit = c->opt_query_limit >= 0 ? (int)std::min<int64_t>(c->opt_query_limit, INT_MAX) : INT_MAX;
+    a.c_pts = cj.sorted.as<float4>();
+    a.c_r2 = cj.sorted_r2.as<float>();
+    a.c_cell_start = cj.cell_start.as<uint32_t>();
+    a.hkeys = cj.hkeys.as<Key>();
+    a.hvals = cj.hvals.as<uint32_t>();
+    a.hash_log2 = cj.hash_log2;
+    a.same_set = si == sj;
+    a.max_coord = gp.max_coord;
+    a.r2_fixed = c->radius_sq;
+    a.ragged = ps.d_ragged.as<int32_t>();
+    a.capacity = ps.capacity;
+    a.list_pos = ps.d_list_pos.as<long long>();
+    a.cursor = &d_cnt->cursor;
+    a.ticket = &d_cnt->ticket;
+    a.n_neighbors = &d_cnt->n_neighbors;
+    a.nb_min = &d_cnt->nb_min;
+    a.nb_max = &d_cnt->nb_max;
+    a.overflow = &d_cnt->overflow;
+    const bool variable = !c->radius_set;
+    const bool symmetric = variable && c->symmetric;   // TreeNSearch.cpp:2431
+    // register slots for the candidate list: 27 cells of average population
+    const double avg_cell = cj.n_cells > 0 ? (double)cj.n / cj.n_cells : 0.0;
+    const int grid = 2 * c->n_sms;
+    cudaError_t e;
+    if (27.0 * avg_cell * 1.15 <= 256.0) e = launch_query<Key, 8>(a, variable, symmetric, grid, c->stream);
+    else e = launch_query<Key, 16>(a, variable, symmetric, grid, c->stream);
+    TNSB_CUDA(c, e);
+    c->stats.n_kernel_launches++;
+    c->stats.n_query_launches++;
+    return TNSB_OK;
+}
+
+double ms_since(const std::chrono::steady_clock::time_point& t0)
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// upload + world box + grid parameters + sorted grid of every set.  Shared by run() and prepare_zsort().
+int build_grid(tnsb_context* c, GridParams* gp_out)
+{
+    cudaStream_t s = c->stream;
+    const int n_sets = (int)c->sets.size();
+    TNSB_CUDA(c, c->h_small.ensure(4096));
+    TNSB_CUDA(c, c->d_reduce.ensure(64));
+    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_BEGIN], s));
+
+    // ---- upload (or adopt device pointers)
+    const void* raw_pts[64];
+    const void* raw_radii[64];
+    for (int si = 0; si < n_sets; si++) {
+        auto& st = c->sets[si];
+        st.sorted_valid = false;
+        const size_t esz = st.is_f64 ? 8 : 4;
+        const void* up = st.is_f64 ? (const void*)st.u_pts_f64 : (const void*)st.u_pts_f32;
+        const void* ur = st.is_f64 ? (const void*)st.u_radii_f64 : (const void*)st.u_radii_f32;
+        if (st.n > 0 && !up) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: point set " + std::to_string(si) + " has a null coordinate pointer.");
+        if (st.n > 0 && st.has_radii && !ur) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: point set " + std::to_string(si) + " has a null radii pointer.");
+        int rc = stage_input(c, up, esz * 3 * (size_t)st.n, st.up_pts, &raw_pts[si]);
+        if (rc != TNSB_OK) return rc;
+        rc = stage_input(c, st.has_radii ? ur : nullptr, esz * (size_t)st.n, st.up_radii, &raw_radii[si]);
+        if (rc != TNSB_OK) return rc;
+    }
+    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_UPLOAD], s));
+
+    // ---- world box + radius range (and double -> float conversion)
+    uint32_t* h_red = c->h_small.as<uint32_t>();
+    for (int k = 0; k < 8; k++) h_red[k] = ((k < 3) || (k == 6)) ? 0xffffffffu : 0u;
+    TNSB_CUDA(c, cudaMemcpyAsync(c->d_reduce.p, h_red, 32, cudaMemcpyHostToDevice, s));
+    const int aabb_grid = 4 * c->n_sms;
+    for (int si = 0; si < n_sets; si++) {
+        auto& st = c->sets[si];
+        if (st.n == 0) { st.d_pts = nullptr; st.d_radii = nullptr; continue; }
+        if (st.is_f64) {
+            TNSB_CUDA(c, st.cv_pts.ensure(sizeof(float) * 3 * (size_t)st.n, 1.1));
+            if (st.has_radii) TNSB_CUDA(c, st.cv_radii.ensure(sizeof(float) * (size_t)st.n, 1.1));
+            aabb_kernel<double><<<aabb_grid, kAabbThreads, 0, s>>>((const double*)raw_pts[si], st.has_radii ? (const double*)raw_radii[si] : nullptr, st.n,
+                                                                  st.cv_pts.as<float>(), st.has_radii ? st.cv_radii.as<float>() : nullptr, c->d_reduce.as<uint32_t>());
+            st.d_pts = st.cv_pts.as<float>();
+            st.d_radii = st.has_radii ? st.cv_radii.as<float>() : nullptr;
+        } else {
+            aabb_kernel<float><<<aabb_grid, kAabbThreads, 0, s>>>((const float*)raw_pts[si], st.has_radii ? (const float*)raw_radii[si] : nullptr, st.n, nullptr, nullptr,
+                                                                 c->d_reduce.as<uint32_t>());
+            st.d_pts = (const float*)raw_pts[si];
+            st.d_radii = st.has_radii ? (const float*)raw_radii[si] : nullptr;
+        }
+        c->stats.n_kernel_launches++;
+    }
+    TNSB_CUDA(c, cudaMemcpyAsync(h_red + 8, c->d_reduce.p, 32, cudaMemcpyDeviceToHost, s));
+    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_AABB], s));
+    TNSB_CUDA(c, cudaStreamSynchronize(s));
+    float lo[3], hi[3];
+    for (int d = 0; d < 3; d++) { lo[d] = ordered_to_float(h_red[8 + d]); hi[d] = ordered_to_float(h_red[8 + 3 + d]); }
+    double r_max = c->radius_set ? (double)c->radius : (double)ordered_to_float(h_red[8 + 7]);
+    for (int d = 0; d < 3; d++)
+        if (!std::isfinite(lo[d]) || !std::isfinite(hi[d])) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: point coordinates are not finite.");
+    if (!c->radius_set && !(r_max > 0.0 && std::isfinite(r_max))) return fail(c, TNSB_ERR_INVALID_STATE, "tnsb: search radii must be positive and finite.");
+
+    // ---- grid: cell edge slightly above the largest search distance, so that the 27-cell stencil is complete
+    const double cell = r_max * (1.0 + 1.0 / 8192.0);
+    bool keep = c->domain_valid && c->cell == cell;
+    if (keep)
+        for (int d = 0; d < 3; d++) keep = keep && c->dom_bottom[d] <= (double)lo[d] && (double)hi[d] <= c->dom_top[d];
+    if (!keep) {
+        // cubic, power-of-two number of cells, enlarged by 10 % so that it survives several time steps (TreeNSearch.cpp:484-521)
+        double length = 0.0;
+        for (int d = 0; d < 3; d++) length = std::max(length, (double)hi[d] - (double)lo[d]);
+        length = (length + 100.0 * 1.1920929e-07) * 1.1;
+        const double n_cells_f = std::floor(length / cell) + 1.0;
+        int bits = 0;
+        while ((double)(1ll << bits) < n_cells_f && bits < 40) bits++;
+        if (bits > Morton<uint64_t>::kMaxBits)
+            return fail(c, TNSB_ERR_LIMIT, "TreeNSearch error: Max allowed cells per dimension is 2097152 (2^21); the search radius is too small for the extent of the point cloud.");
+        const double full = cell * (double)(1ll << bits);
+        for (int d = 0; d < 3; d++) {
+            const double center = 0.5 * ((double)hi[d] + (double)lo[d]);
+            c->dom_bottom[d] = center - 0.5 * full;
+            c->dom_top[d] = center + 0.5 * full;
+        }
+        c->cell = cell;
+        c->bits = bits;
+        c->key64 = bits > Morton<uint32_t>::kMaxBits;
+        c->domain_valid = true;
+    }
+    GridParams gp;
+    for (int d = 0; d < 3; d++) gp.bottom[d] = c->dom_bottom[d];
+    gp.inv_cell = 1.0 / c->cell;
+    gp.bits = c->bits;
+    gp.max_coord = (int)((1ll << c->bits) - 1);
+    *gp_out = gp;
+    c->stats.cell_size = (float)c->cell;
+    c->stats.key_bits = 3 * c->bits;
+    for (int d = 0; d < 3; d++) { c->stats.domain_bottom[d] = (float)c->dom_bottom[d]; c->stats.domain_top[d] = (float)c->dom_top[d]; }
+
+    return c->key64 ? build_sets<uint64_t>(c, gp) : build_sets<uint32_t>(c, gp);
+}
+
+float ev_ms(tnsb_context* c, int a, int b)
+{
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]) != cudaSuccess) { cudaGetLastError(); return 0.0f; }
+    return ms;
+}
+
+int run_impl(tnsb_context* c)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = validate(c);
+    if (rc != TNSB_OK) return rc;
+    TNSB_CUDA(c, cudaSetDevice(c->device));
+    memset(&c->stats, 0, sizeof(c->stats));
+    const int n_sets = (int)c->sets.size();
+    if (n_sets > 64) return fail(c, TNSB_ERR_LIMIT, "tnsb: at most 64 point sets are supported.");
+    c->pairs.resize((size_t)n_sets * n_sets);
+    for (auto& p : c->pairs) { p.valid = false; p.host_valid = false; p.n_ints = 0; p.n_neighbors = 0; p.n_lists = 0; }
+    int64_t n_total = 0;
+    for (auto& st : c->sets) n_total += st.n;
+    c->stats.n_points_total = n_total;
+    cudaStream_t s = c->stream;
+
+    GridParams gp;
+    memset(&gp, 0, sizeof(gp));
+    if (n_total > 0) {
+        rc = build_grid(c, &gp);
+        if (rc != TNSB_OK) return rc;
+    } else {
+        for (int k = 0; k < EV_COUNT; k++) TNSB_CUDA(c, cudaEventRecord(c->ev[k], s));
+    }
+
+    // ---- queries, one launch per active ordered pair
+    std::vector<int> act;
+    for (int si = 0; si < n_sets; si++)
+        for (int sj = 0; sj < n_sets; sj++)
+            if (c->active[si][sj]) act.push_back(si * n_sets + sj);
+    const size_t n_pairs = (size_t)n_sets * n_sets;
+    TNSB_CUDA(c, c->d_counters.ensure(sizeof(PairCounters) * std::max<size_t>(n_pairs, 1)));
+    TNSB_CUDA(c, c->h_small.ensure(4096 + 2 * sizeof(PairCounters) * std::max<size_t>(n_pairs, 1)));
+    PairCounters* h_init = reinterpret_cast<PairCounters*>(c->h_small.as<char>() + 2048);
+    PairCounters* h_out = h_init + std::max<size_t>(n_pairs, 1);
+    const int qlimit = c->opt_query_limit >= 0 ? (int)std::min<int64_t>(c->opt_query_limit, INT_MAX) : INT_MAX;
+
+    std::vector<int> todo;
+    for (int id : act) {
+        const int si = id / n_sets;
+        PairState& ps = c->pairs[id];
+        ps.n_lists = std::min(c->sets[si].n, qlimit);
+        ps.valid = true;
+        if (c->sets[si].n == 0 || n_total == 0) continue;
+        const int64_t want = (int64_t)ps.n_lists * (c->opt_list_capacity + 1) + 4096;
+        if (ps.capacity < want) {
+            TNSB_CUDA(c, ps.d_ragged.ensure(sizeof(int32_t) * (size_t)want));
+            ps.capacity = (int64_t)(ps.d_ragged.cap / sizeof(int32_t));
+        }
+        TNSB_CUDA(c, ps.d_list_pos.ensure(sizeof(long long) * (size_t)c->sets[si].n, 1.1));
+        todo.push_back(id);
+    }
+    int attempts = 0;
+    while (!todo.empty()) {
+        if (++attempts > 4) return fail(c, TNSB_ERR_LIMIT, "tnsb: neighbour list buffer kept overflowing.");
+        for (int id : todo) {
+            PairCounters z;
+            memset(&z, 0, sizeof(z));
+            z.nb_min = INT_MAX;
+            h_init[id] = z;
+        }
+        for (int id : todo)
+            TNSB_CUDA(c, cudaMemcpyAsync(c->d_counters.as<PairCounters>() + id, h_init + id, sizeof(PairCounters), cudaMemcpyHostToDevice, s));
+        for (int id : todo) {
+            const int si = id / n_sets, sj = id % n_sets;
+            rc = c->key64 ? query_pair<uint64_t>(c, si, sj, gp, c->d_counters.as<PairCounters>() + id)
+                          : query_pair<uint32_t>(c, si, sj, gp, c->d_counters.as<PairCounters>() + id);
+            if (rc != TNSB_OK) return rc;
+        }
+        TNSB_CUDA(c, cudaMemcpyAsync(h_out, c->d_counters.p, sizeof(PairCounters) * n_pairs, cudaMemcpyDeviceToHost, s));
+        TNSB_CUDA(c, cudaStreamSynchronize(s));
+        std::vector<int> again;
+        for (int id : todo) {
+            PairState& ps = c->pairs[id];
+            const PairCounters& r = h_out[id];
+            if (r.overflow) {
+                // the cursor kept counting: it is the exact size needed
+                const size_t need = (size_t)((double)r.cursor * 1.1) + 4096;
+                TNSB_CUDA(c, ps.d_ragged.ensure(sizeof(int32_t) * need));
+                ps.capacity = (int64_t)(ps.d_ragged.cap / sizeof(int32_t));
+                again.push_back(id);
+                c->stats.n_reruns++;
+            } else {
+                ps.n_ints = (int64_t)r.cursor;
+                ps.n_neighbors = (int64_t)r.n_neighbors;
+                ps.nb_min = r.nb_min == INT_MAX ? 0 : r.nb_min;
+                ps.nb_max = r.nb_max;
+            }
+        }
+        todo.swap(again);
+    }
+    if (c->opt_sort_lists) {
+        for (int id : act) {
+            PairState& ps = c->pairs[id];
+            if (ps.n_lists == 0 || ps.n_ints == 0) continue;
+            const int64_t threads = (int64_t)ps.n_lists * 32;
+            sort_lists_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, s>>>(ps.d_ragged.as<int32_t>(), ps.d_list_pos.as<long long>(), ps.n_lists, qlimit);
+            c->stats.n_kernel_launches++;
+        }
+        TNSB_CUDA(c, cudaGetLastError());
+    }
+    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_QUERY], s));
+
+    // ---- host mirror of the lists
+    for (int id : act) {
+        PairState& ps = c->pairs[id];
+        const int si = id / n_sets;
+        c->stats.n_queries += ps.n_lists;
+        c->stats.n_neighbors += ps.n_neighbors;
+        c->stats.n_list_ints += ps.n_ints;
+        if (!c->opt_host_results || ps.n_lists == 0) continue;
+        TNSB_CUDA(c, ps.h_ragged.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(ps.n_ints, 1), 1.25));
+        TNSB_CUDA(c, ps.h_list_pos.ensure(sizeof(long long) * (size_t)c->sets[si].n, 1.25));
+        TNSB_CUDA(c, cudaMemcpyAsync(ps.h_ragged.p, ps.d_ragged.p, sizeof(int32_t) * (size_t)ps.n_ints, cudaMemcpyDeviceToHost, s));
+        TNSB_CUDA(c, cudaMemcpyAsync(ps.h_list_pos.p, ps.d_list_pos.p, sizeof(long long) * (size_t)ps.n_lists, cudaMemcpyDeviceToHost, s));
+        c->stats.d2h_bytes += (int64_t)sizeof(int32_t) * ps.n_ints + (int64_t)sizeof(long long) * ps.n_lists;
+        ps.host_valid = true;
+    }
+    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_DOWNLOAD], s));
+    TNSB_CUDA(c, cudaStreamSynchronize(s));
+
+    c->stats.ms_upload = ev_ms(c, EV_BEGIN, EV_UPLOAD);
+    c->stats.ms_aabb = ev_ms(c, EV_UPLOAD, EV_AABB);
+    c->stats.ms_keys = ev_ms(c, EV_AABB, EV_KEYS);
+    c->stats.ms_sort = ev_ms(c, EV_KEYS, EV_SORT);
+    c->stats.ms_reorder = ev_ms(c, EV_SORT, EV_REORDER);
+    c->stats.ms_cells = ev_ms(c, EV_REORDER, EV_CELLS);
+    c->stats.ms_query = ev_ms(c, EV_CELLS, EV_QUERY);
+    c->stats.ms_download = ev_ms(c, EV_QUERY, EV_DOWNLOAD);
+    c->stats.ms_total_device = ev_ms(c, EV_UPLOAD, EV_QUERY);
+    c->stats.ms_wall = ms_since(t0);
+    return TNSB_OK;
+}
+
+int check_set(tnsb_context* c, int s, const char* who)
+{
+    if (!c) return TNSB_ERR_INVALID_ARGUMENT;
+    if (s < 0 || s >= (int)c->sets.size()) return fail(c, TNSB_ERR_INVALID_ARGUMENT, std::string(who) + " error: set does not exist.");
+    return TNSB_OK;
+}
+
+int new_point_set(tnsb_context* c, int n)
+{
+    // TreeNSearch::_new_point_set, TreeNSearch.cpp:346-365
+    if (n < 0) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: negative number of points.");
+    c->sets.emplace_back();
+    c->sets.back().n = n;
+    for (auto& row : c->active) row.push_back(0);
+    c->active.emplace_back(c->sets.size(), (uint8_t)0);
+    return (int)c->sets.size() - 1;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+const char* tnsb_version(void) { return "treensearch_b200 0.1 (sm_100a)"; }
+
+int tnsb_create(tnsb_context** out, int device)
+{
+    if (!out) return TNSB_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        g_create_error = std::string("tnsb: no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                         "); this engine has no CPU fallback.";
+        return TNSB_ERR_NO_DEVICE;
+    }
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) { cudaGetLastError(); device = 0; }
+    }
+    if (device >= count) { g_create_error = "tnsb: device index out of range."; return TNSB_ERR_INVALID_ARGUMENT; }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = std::string("tnsb: cudaSetDevice failed: ") + cudaGetErrorString(e); return TNSB_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return TNSB_ERR_CUDA; }
+    if (prop.major < 10) {
+        g_create_error = "tnsb: this library is built for sm_100a (B200) only; found compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor);
+        return TNSB_ERR_NO_DEVICE;
+    }
+    tnsb_context* c = new tnsb_context();
+    c->device = device;
+    c->n_sms = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = std::string("tnsb: cudaStreamCreate failed: ") + cudaGetErrorString(e);
+        delete c;
+        return TNSB_ERR_CUDA;
+    }
+    c->own_stream = c->stream;
+    for (int k = 0; k < EV_COUNT; k++) cudaEventCreate(&c->ev[k]);
+    *out = c;
+    return TNSB_OK;
+}
+
+void tnsb_destroy(tnsb_context* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& kv : c->registered) cudaHostUnregister(const_cast<void*>(kv.first));
+    for (auto& st : c->sets) {
+        st.up_pts.release(); st.up_radii.release(); st.cv_pts.release(); st.cv_radii.release();
+        for (int b = 0; b < 2; b++) { st.keys[b].release(); st.vals[b].release(); }
+        st.sorted.release(); st.sorted_r2.release(); st.cell_key.release(); st.cell_start.release(); st.tile_heads.release();
+        st.hkeys.release(); st.hvals.release(); st.d_zorder.release();
+    }
+    for (auto& p : c->pairs) { p.d_ragged.release(); p.d_list_pos.release(); p.h_ragged.release(); p.h_list_pos.release(); }
+    c->d_reduce.release(); c->d_counters.release(); c->d_misc.release(); c->sort_temp.release(); c->scan_temp.release(); c->h_small.release();
+    for (int k = 0; k < EV_COUNT; k++) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+const char* tnsb_last_error(const tnsb_context* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+// ---- point sets -------------------------------------------------------------------------------------------------------
+int tnsb_add_point_set_f32(tnsb_context* c, const float* pts, const float* radii, int n, int variable_radius)
+{
+    if (!c) return TNSB_ERR_INVALID_ARGUMENT;
+    const int s = new_point_set(c, n);
+    if (s < 0) return s;
+    auto& st = c->sets[s];
+    st.u_pts_f32 = pts; st.u_radii_f32 = variable_radius ? radii : nullptr; st.is_f64 = false;
+    st.has_radii = variable_radius != 0;
+    if (st.has_radii) c->n_sets_with_radii++;      // set_radii.push_back, TreeNSearch.cpp:53
+    return s;
+}
+
+int tnsb_add_point_set_f64(tnsb_context* c, const double* pts, const double* radii, int n, int variable_radius)
+{
+    if (!c) return TNSB_ERR_INVALID_ARGUMENT;
+    const int s = new_point_set(c, n);
+    if (s < 0) return s;
+    auto& st = c->sets[s];
+    st.u_pts_f64 = pts; st.u_radii_f64 = variable_radius ? radii : nullptr; st.is_f64 = true;
+    st.has_radii = variable_radius != 0;
+    if (st.has_radii) c->n_sets_with_radii++;
+    return s;
+}
+
+static int resize_common(tnsb_context* c, int s, int n, bool with_radii)
+{
+    if (!c) return TNSB_ERR_INVALID_ARGUMENT;
+    if (s < 0 || s >= (int)c->sets.size())      // TreeNSearch.cpp:69-72
+        return fail(c, TNSB_ERR_INVALID_ARGUMENT, "TreeNSearch::resize_point_set error: Cannot resize a set that was not previously added.");
+    if (n < 0) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: negative number of points.");
+    if (with_radii && c->n_sets_with_radii == 0)   // TreeNSearch.cpp:73-76
+        return fail(c, TNSB_ERR_INVALID_STATE, "TreeNSearch::resize_point_set error: Cannot resize a set with a radii array if it previously didn't have one.");
+    return TNSB_OK;
+}
+
+int tnsb_resize_point_set_f32(tnsb_context* c, int s, const float* pts, const float* radii, int n, int variable_radius)
+{
+    int rc = resize_common(c, s, n, variable_radius != 0);
+    if (rc != TNSB_OK) return rc;
+    auto& st = c->sets[s];
+    st.u_pts_f32 = pts; st.u_pts_f64 = nullptr;
+    if (variable_radius) { st.u_radii_f32 = radii; st.u_radii_f64 = nullptr; }
+    else if (st.is_f64) { st.u_radii_f32 = nullptr; st.u_radii_f64 = nullptr; }
+    st.is_f64 = false;
+    st.n = n;
+    st.sorted_valid = false;     // TreeNSearch.cpp:118
+    return TNSB_OK;
+}
+
+int tnsb_resize_point_set_f64(tnsb_context* c, int s, const double* pts, const double* radii, int n, int variable_radius)
+{
+    int rc = resize_common(c, s, n, variable_radius != 0);
+    if (rc != TNSB_OK) return rc;
+    auto& st = c->sets[s];
+    st.u_pts_f64 = pts; st.u_pts_f32 = nullptr;
+    if (variable_radius) { st.u_radii_f64 = radii; st.u_radii_f32 = nullptr; }
+    else if (!st.is_f64) { st.u_radii_f32 = nullptr; st.u_radii_f64 = nullptr; }
+    st.is_f64 = true;
+    st.n = n;
+    st.sorted_valid = false;
+    return TNSB_OK;
+}
+
+// ---- configuration ------------------------------------------------------------------------------------------------------
+int tnsb_set_search_radius(tnsb_context* c, float r)
+{
+    if (!c) return TNSB_ERR_INVALID_ARGUMENT;
+    if (c->n_sets_with_radii > 0)   // TreeNSearch.cpp:22-25
+        return fail(c, TNSB_ERR_INVALID_STATE, "tns::TreeNSearch::set_search_radius error: Cannot set a global search radius if a set with a radii array was already added.");
+    c->radius_set = true;
+    c->radius = r;
+    c->radius_sq = r * r;           // float product, TreeNSearch.cpp:29
+    return TNSB_OK;
+}
+
+int tnsb_set_cell_size(tnsb_context* c, float cell_size)
+{
+    if (!c) return TNSB_ERR_INVALID_ARGUMENT;
+    if (c->user_cell_size > 0.0f)   // TreeNSearch.cpp:175-178
+        return fail(c, TNSB_ERR_INVALID_STATE, "tns::TreeNSearch::set_cell_size error: Cell size already set. Create a new TreeNSearch instance if you need a different cell_size.");
+    c->user_cell_size = cell_size;
+    return TNSB_OK;
+}
+
+int tnsb_set_symmetric_search(tnsb_context* c, int active)
+{
+    if (!c) return TNSB_ERR_INVALID_ARGUMENT;
+    c->symmetric = active != 0;
+    return TNSB_OK;
+}
+
+int tnsb_set_active_search(tnsb_context* c, int si, int sj, int active)
+{
+    int rc = check_set(c, si, "TreeNSearch::set_active_search");
+    if (rc == TNSB_OK) rc = check_set(c, sj, "TreeNSearch::set_active_search");
+    if (rc != TNSB_OK) return rc;
+    c->active[si][sj] = active ? 1 : 0;
+    return TNSB_OK;
+}
+
+int tnsb_set_active_search_of_set(tnsb_context* c, int si, int search_neighbors, int find_neighbors)
+{
+    int rc = check_set(c, si, "TreeNSearch::set_active_search");
+    if (rc != TNSB_OK) return rc;
+    // order matters (TreeNSearch.cpp:225-235): the find column first, then the search row
+    for (size_t sj = 0; sj < c->sets.size(); sj++) c->active[sj][si] = find_neighbors ? 1 : 0;
+    for (size_t sj = 0; sj < c->sets.size(); sj++) c->active[si][sj] = search_neighbors ? 1 : 0;
+    return TNSB_OK;
+}
+
+int tnsb_set_all_searches(tnsb_context* c, int active)
+{
+    if (!c) return TNSB_ERR_INVALID_ARGUMENT;
+    for (auto& row : c->active) std::fill(row.begin(), row.end(), (uint8_t)(active ? 1 : 0));
+    return TNSB_OK;
+}
+
+int tnsb_set_option(tnsb_context* c, int option, int64_t value)
+{
+    if (!c) return TNSB_ERR_INVALID_ARGUMENT;
+    switch (option) {
+    case TNSB_OPT_HOST_RESULTS: c->opt_host_results = value != 0; return TNSB_OK;
+    case TNSB_OPT_PIN_USER_MEMORY: c->opt_pin_user = value != 0; return TNSB_OK;
+    case TNSB_OPT_LIST_CAPACITY:
+        if (value < 1) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: list capacity must be >= 1.");
+        c->opt_list_capacity = value; return TNSB_OK;
+    case TNSB_OPT_QUERY_LIMIT: c->opt_query_limit = value; return TNSB_OK;
+    case TNSB_OPT_SORT_LISTS: c->opt_sort_lists = value != 0; return TNSB_OK;
+    default: return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: unknown option.");
+    }
+}
+
+int tnsb_set_stream(tnsb_context* c, void* cuda_stream)
+{
+    if (!c) return TNSB_ERR_INVALID_ARGUMENT;
+    cudaStreamSynchronize(c->stream);
+    c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return TNSB_OK;
+}
+
+// ---- getters ------------------------------------------------------------------------------------------------------------
+int tnsb_get_n_sets(const tnsb_context* c) { return c ? (int)c->sets.size() : 0; }
+int tnsb_get_n_points_in_set(const tnsb_context* c, int s) { return (c && s >= 0 && s < (int)c->sets.size()) ? c->sets[s].n : -1; }
+int tnsb_get_total_n_points(const tnsb_context* c)
+{
+    int t = 0;
+    if (c) for (auto& st : c->sets) t += st.n;
+    return t;
+}
+int tnsb_is_search_active(const tnsb_context* c, int si, int sj)
+{
+    if (!c || si < 0 || sj < 0 || si >= (int)c->sets.size() || sj >= (int)c->sets.size()) return 0;
+    return c->active[si][sj];
+}
+int tnsb_does_set_exist(const tnsb_context* c, int s) { return (c && s >= 0 && s < (int)c->sets.size()) ? 1 : 0; }
+
+// ---- hot path -----------------------------------------------------------------------------------------------------------
+int tnsb_run(tnsb_context* c)
+{
+    if (!c) return TNSB_ERR_INVALID_ARGUMENT;
+    return run_impl(c);
+}
+
+int tnsb_get_neighborlists(const tnsb_context* c, int si, int sj, const int32_t** ragged, const int64_t** list_pos, int64_t* n_ints)
+{
+    if (!c || si < 0 || sj < 0 || si >= (int)c->sets.size() || sj >= (int)c->sets.size()) return TNSB_ERR_INVALID_ARGUMENT;
+    const size_t id = (size_t)si * c->sets.size() + sj;
+    if (id >= c->pairs.size() || !c->pairs[id].valid) {
+        const_cast<tnsb_context*>(c)->err = "TreeNSearch::get_neighborlist error: Set pair not active (or run() not called).";
+        return TNSB_ERR_INVALID_STATE;
+    }
+    const PairState& ps = c->pairs[id];
+    if (ps.n_lists > 0 && !ps.host_valid) {
+        const_cast<tnsb_context*>(c)->err = "tnsb: host results are disabled (TNSB_OPT_HOST_RESULTS = 0); use tnsb_get_neighborlists_device.";
+        return TNSB_ERR_INVALID_STATE;
+    }
+    if (ragged) *ragged = ps.h_ragged.as<int32_t>();
+    if (list_pos) *list_pos = ps.h_list_pos.as<int64_t>();
+    if (n_ints) *n_ints = ps.n_ints;
+    return TNSB_OK;
+}
+
+int tnsb_get_neighborlists_device(const tnsb_context* c, int si, int sj, const int32_t** ragged, const int64_t** list_pos, int64_t* n_ints)
+{
+    if (!c || si < 0 || sj < 0 || si >= (int)c->sets.size() || sj >= (int)c->sets.size()) return TNSB_ERR_INVALID_ARGUMENT;
+    const size_t id = (size_t)si * c->sets.size() + sj;
+    if (id >= c->pairs.size() || !c->pairs[id].valid) {
+        const_cast<tnsb_context*>(c)->err = "TreeNSearch::get_neighborlist error: Set pair not active (or run() not called).";
+        return TNSB_ERR_INVALID_STATE;
+    }
+    const PairState& ps = c->pairs[id];
+    if (ragged) *ragged = ps.d_ragged.as<int32_t>();
+    if (list_pos) *list_pos = ps.d_list_pos.as<int64_t>();
+    if (n_ints) *n_ints = ps.n_ints;
+    return TNSB_OK;
+}
+
+int tnsb_prepare_zsort(tnsb_context* c)
+{
+    if (!c) return TNSB_ERR_INVALID_ARGUMENT;
+    int rc = validate(c);
+    if (rc != TNSB_OK) return rc;
+    TNSB_CUDA(c, cudaSetDevice(c->device));
+    bool all_valid = true;
+    int64_t n_total = 0;
+    for (auto& st : c->sets) { all_valid = all_valid && (st.sorted_valid || st.n == 0); n_total += st.n; }
+    if (!all_valid && n_total > 0) {
+        // no grid of the current points yet (TreeNSearch.cpp:2592-2595): build it now
+        GridParams gp;
+        memset(&c->stats, 0, sizeof(c->stats));
+        rc = build_grid(c, &gp);
+        if (rc != TNSB_OK) return rc;
+    }
+    for (auto& st : c->sets) {
+        st.zsort_new_to_old.resize((size_t)st.n);
+        if (st.n == 0) { st.zorder_ready = true; continue; }
+        TNSB_CUDA(c, st.d_zorder.ensure(sizeof(int32_t) * (size_t)st.n, 1.1));
+        TNSB_CUDA(c, cudaMemcpyAsync(st.d_zorder.p, st.vals[st.sel].p, sizeof(int32_t) * (size_t)st.n, cudaMemcpyDeviceToDevice, c->stream));
+        TNSB_CUDA(c, cudaMemcpyAsync(st.zsort_new_to_old.data(), st.vals[st.sel].p, sizeof(int32_t) * (size_t)st.n, cudaMemcpyDeviceToHost, c->stream));
+        st.zorder_ready = true;
+        st.sorted_valid = false;      // TreeNSearch.cpp:2660: the user is about to permute the arrays
+    }
+    TNSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TNSB_OK;
+}
+
+int tnsb_get_zsort_order(const tnsb_context* c, int s, const int32_t** new_to_old, int* n_points)
+{
+    if (!c || s < 0 || s >= (int)c->sets.size()) return TNSB_ERR_INVALID_ARGUMENT;
+    const SetState& st = c->sets[s];
+    if (!st.zorder_ready || (int)st.zsort_new_to_old.size() != st.n) {
+        const_cast<tnsb_context*>(c)->err = "tns::TreeNSearch::apply_zsort error: no zsort order ready for set_i (" + std::to_string(s) + ").";
+        return TNSB_ERR_INVALID_STATE;
+    }
+    if (new_to_old) *new_to_old = st.zsort_new_to_old.data();
+    if (n_points) *n_points = st.n;
+    return TNSB_OK;
+}
+
+int tnsb_apply_zsort_device_f32(tnsb_context* c, int s, float* d_data, int stride)
+{
+    int rc = check_set(c, s, "tns::TreeNSearch::apply_zsort");
+    if (rc != TNSB_OK) return rc;
+    SetState& st = c->sets[s];
+    if (!st.zorder_ready) return fail(c, TNSB_ERR_INVALID_STATE, "tns::TreeNSearch::apply_zsort error: no zsort order ready for set_i (" + std::to_string(s) + ").");
+    if (st.n == 0 || stride <= 0) return TNSB_OK;
+    if (!is_device_pointer(d_data)) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb_apply_zsort_device_f32: data must be device memory.");
+    TNSB_CUDA(c, cudaSetDevice(c->device));
+    const size_t bytes = sizeof(float) * (size_t)st.n * stride;
+    TNSB_CUDA(c, c->scan_temp.ensure(bytes, 1.1));
+    TNSB_CUDA(c, cudaMemcpyAsync(c->scan_temp.p, d_data, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    const int64_t total = (int64_t)st.n * stride;
+    gather_rows_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, c->stream>>>(c->scan_temp.as<float>(), d_data, st.d_zorder.as<int32_t>(), st.n, stride);
+    TNSB_CUDA(c, cudaGetLastError());
+    TNSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TNSB_OK;
+}
+
+// ---- diagnostics --------------------------------------------------------------------------------------------------------
+uint64_t tnsb_get_neighborlist_n_bytes(const tnsb_context* c)
+{
+    uint64_t b = 0;
+    if (c) for (auto& p : c->pairs) if (p.valid) b += (uint64_t)p.n_ints * sizeof(int32_t);
+    return b;
+}
+
+int tnsb_get_stats(const tnsb_context* c, tnsb_stats* out)
+{
+    if (!c || !out) return TNSB_ERR_INVALID_ARGUMENT;
+    *out = c->stats;
+    return TNSB_OK;
+}
+
+int tnsb_get_pair_neighbor_stats(const tnsb_context* c, int si, int sj, int64_t out[3])
+{
+    if (!c || !out || si < 0 || sj < 0 || si >= (int)c->sets.size() || sj >= (int)c->sets.size()) return TNSB_ERR_INVALID_ARGUMENT;
+    const size_t id = (size_t)si * c->sets.size() + sj;
+    if (id >= c->pairs.size() || !c->pairs[id].valid) return TNSB_ERR_INVALID_STATE;
+    out[0] = c->pairs[id].nb_min; out[1] = c->pairs[id].nb_max; out[2] = c->pairs[id].n_neighbors;
+    return TNSB_OK;
+}
+
+}  // extern "C"
