@@ -80,6 +80,7 @@ class TreeNSearch:
         self._keep = {}              # set id -> (points, radii) keep-alive of the borrowed arrays
         self._n_threads = -1
         self._views = {}
+        self._query_limit = -1
 
     # ------------------------------------------------------------------ plumbing
     def close(self):
@@ -149,6 +150,8 @@ class TreeNSearch:
             n_ints = C.c_int64()
             self._check(self._lib.tnsb_get_neighborlists(self._h, set_i, set_j, C.byref(rag), C.byref(pos), C.byref(n_ints)))
             n_i = self.get_n_points_in_set(set_i)
+            if self._query_limit >= 0:
+                n_i = min(n_i, self._query_limit)      # find-only (halo) points have no list
             ragged = np.ctypeslib.as_array(rag, shape=(max(n_ints.value, 1),))[: n_ints.value] if n_ints.value > 0 else np.zeros(0, np.int32)
             list_pos = np.ctypeslib.as_array(pos, shape=(max(n_i, 1),))[:n_i] if n_i > 0 else np.zeros(0, np.int64)
             v = (ragged, list_pos)
@@ -272,6 +275,8 @@ class TreeNSearch:
     # ------------------------------------------------------------------ engine extras (not in the reference)
     def set_option(self, option, value):
         self._check(self._lib.tnsb_set_option(self._h, int(option), int(value)))
+        if int(option) == L.TNSB_OPT_QUERY_LIMIT:
+            self._query_limit = int(value)
 
     def set_stream(self, cuda_stream):
         """Run on the caller's CUDA stream (an int cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream); 0/None = own stream."""

@@ -6,10 +6,11 @@
 //   * lanes 0..26 look the 27 neighbour cells of set_j up in the cell hash and a warp scan turns their populations into a
 //     dense candidate list; every lane then owns candidate t = slot*32 + lane and keeps it in REGISTERS for the whole cell
 //     (one coalesced 16-byte load per candidate per cell, instead of one per (query, candidate) pair);
-//   * for each query point of the cell (broadcast with shuffles) every lane tests its candidates with the reference's exact
-//     arithmetic  d2 = fma(dz,dz, fma(dx,dx, dy*dy)) <= r^2  (TreeNSearch.cpp:2477-2486 as compiled),
-//     a warp scan of the per-lane hit counts gives the list size and every lane's slot, hits are compacted into a per-warp
-//     shared-memory staging buffer as  [n, j0, j1, ...]  (the reference's list layout, TreeNSearch.h:395);
+//   * for each query point of the cell (broadcast from shared memory) every lane tests its candidates, two per instruction
+//     with Blackwell's packed FADD2/FMUL2/FFMA2, in the reference's exact arithmetic
+//     d2 = fma(dz,dz, fma(dx,dx, dy*dy)) <= r^2  (TreeNSearch.cpp:2477-2486 as compiled); a warp ballot per
+//     slot compacts the hits straight into a per-warp shared-memory staging buffer as  [n, j0, j1, ...]  (the reference's
+//     list layout, TreeNSearch.h:395) -- no shuffles and no dependent scan chain in the inner loop;
 //   * when the staging buffer is full the warp reserves a range of the global ragged buffer with ONE atomicAdd, copies the
 //     staged lists with fully coalesced stores and publishes list_pos[i] for the staged queries.
 // Lists are therefore written exactly once, in one pass (no count pass), and nothing is ever re-read from HBM.
@@ -17,16 +18,26 @@
 // Self exclusion: only the identical (set, index) is excluded (TreeNSearch.cpp:2464-2466); coincident points are neighbours.
 #pragma once
 #include "common.cuh"
+#include <type_traits>
 
 namespace tnsb {
 
 constexpr int kQueryThreads = 256;
 constexpr int kQueryWarps = kQueryThreads / 32;
-constexpr int kStageInts = 2048;          // per-warp staging capacity (ints)
-constexpr int kStageRecs = 256;           // per-warp staged list records
+constexpr int kQueryBlocksPerSM = 3;
+constexpr int kStageInts = 1536;          // per-warp staging capacity (ints)
+constexpr int kStageRecs = 192;           // per-warp staged list records
 constexpr int kCellsPerTicket = 8;
-constexpr int kWarpSmemInts = kStageInts + 2 * kStageRecs + 64;
+// per-warp shared memory (ints): stage | rec_idx | rec_off | run_start[32] | run_pre[32] | query float4[32] | query r2[32]
+constexpr int kOffRecIdx = kStageInts;
+constexpr int kOffRecOff = kOffRecIdx + kStageRecs;
+constexpr int kOffRunStart = kOffRecOff + kStageRecs;
+constexpr int kOffRunPre = kOffRunStart + 32;
+constexpr int kOffQbuf = kOffRunPre + 32;        // must be a multiple of 4 ints (float4 alignment)
+constexpr int kOffQr2 = kOffQbuf + 128;
+constexpr int kWarpSmemInts = kOffQr2 + 32;
 constexpr int kQuerySmemBytes = kQueryWarps * kWarpSmemInts * 4;
+static_assert(kOffQbuf % 4 == 0 && kWarpSmemInts % 4 == 0, "float4 alignment of the per-warp query buffer");
 
 template <typename Key>
 struct QueryArgs {
@@ -60,9 +71,9 @@ struct QueryArgs {
 };
 
 struct WarpStage {
-    int* ints;       // [kStageInts]
-    int* rec_idx;    // [kStageRecs]
-    int* rec_off;    // [kStageRecs]
+    int* ints;       // [kStageInts]  staged lists  [n, j0, j1, ...]
+    int* rec_idx;    // [kStageRecs]  query index of every staged list
+    int* rec_off;    // [kStageRecs]  its offset inside ints
     int* run_start;  // [32]
     int* run_pre;    // [32]
     int wpos;
@@ -89,8 +100,8 @@ __device__ __forceinline__ void stage_flush(WarpStage& st, const QueryArgs<Key>&
     __syncwarp();
 }
 
-// reserve room for one list of n ids.  Returns the destination of the count word: either inside the staging buffer
-// (global == false) or, for lists that do not fit the staging buffer at all, directly in the ragged buffer.
+// general path only: reserve room for one list of n ids whose size is already known.  Returns the destination of the count
+// word: inside the staging buffer, or -- for lists that do not fit the staging buffer at all -- directly in the ragged buffer.
 template <typename Key>
 __device__ __forceinline__ int* reserve_list(WarpStage& st, const QueryArgs<Key>& a, int lane, int qidx, int n, bool& ok)
 {
@@ -141,6 +152,47 @@ __device__ __forceinline__ float dist2(float qx, float qy, float qz, float cx, f
     return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
+// Blackwell packed fp32 pairs (FADD2 / FMUL2 / FFMA2): two candidates per instruction, each half rounded to nearest exactly
+// like the scalar instruction, so the result is bit-identical to dist2().
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+    f32x2 v;
+    asm volatile("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+    return v;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// x + (-0.0) == x for every x: an exact identity that ptxas cannot fold away, used once per cell to make the candidate
+// pairs live in aligned 64-bit registers (otherwise the halves stay in the LDG.128 destination registers and every FADD2 of
+// the inner loop needs two extra moves to assemble its operand).
+__device__ __forceinline__ f32x2 settle2(f32x2 a)
+{
+    f32x2 r;
+    asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(0x8000000080000000ull));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 // candidate t of the dense list -> position in the sorted array of set_j (5-step search of the 32-entry run table)
 __device__ __forceinline__ int candidate_pos(const WarpStage& st, int t)
 {
@@ -152,22 +204,29 @@ __device__ __forceinline__ int candidate_pos(const WarpStage& st, int t)
 }
 
 template <typename Key, int NSLOT, bool VARIABLE, bool SYMMETRIC>
-__global__ void __launch_bounds__(kQueryThreads, 2) query_kernel(const QueryArgs<Key> a)
+__global__ void __launch_bounds__(kQueryThreads, NSLOT <= 8 ? kQueryBlocksPerSM : 2) query_kernel(const QueryArgs<Key> a)
 {
-    extern __shared__ int s_mem[];
+    static_assert(NSLOT % 2 == 0, "slots are processed in packed pairs");
+    extern __shared__ __align__(16) int s_mem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpStage st;
     st.ints = s_mem + warp * kWarpSmemInts;
-    st.rec_idx = st.ints + kStageInts;
-    st.rec_off = st.rec_idx + kStageRecs;
-    st.run_start = st.rec_off + kStageRecs;
-    st.run_pre = st.run_start + 32;
+    st.rec_idx = st.ints + kOffRecIdx;
+    st.rec_off = st.ints + kOffRecOff;
+    st.run_start = st.ints + kOffRunStart;
+    st.run_pre = st.ints + kOffRunPre;
+    float4* qbuf = reinterpret_cast<float4*>(st.ints + kOffQbuf);
+    float* qr2s = reinterpret_cast<float*>(st.ints + kOffQr2);
     st.wpos = 0;
     st.nrec = 0;
 
     // neighbour cell offset owned by this lane (lanes 27..31 idle during the lookup)
     const int ox = lane % 3 - 1, oy = (lane / 3) % 3 - 1, oz = lane / 9 - 1;
     const uint32_t hmask = (1u << a.hash_log2) - 1u;
+    const unsigned lt = lanemask_lt();
+    const float r2_fixed = a.r2_fixed;
+    const int query_limit = a.query_limit;
+    const bool same_set = a.same_set != 0;
 
     unsigned long long nb_sum = 0;
     int nb_lo = 0x7fffffff, nb_hi = 0;
@@ -213,72 +272,98 @@ __global__ void __launch_bounds__(kQueryThreads, 2) query_kernel(const QueryArgs
             const int self_pre = a.same_set ? st.run_pre[13] : 0;   // lane 13 = offset (0,0,0)
 
             if (T <= NSLOT * 32) {
-                // ---------------- fast path: the whole candidate list lives in registers
-                float px[NSLOT], py[NSLOT], pz[NSLOT];
+                // ---------------- fast path: the whole candidate list lives in registers, two slots per packed register
+                f32x2 px[NSLOT / 2], py[NSLOT / 2], pz[NSLOT / 2];
                 int pid[NSLOT];
                 float pr2[SYMMETRIC ? NSLOT : 1];
 #pragma unroll
-                for (int s = 0; s < NSLOT; s++) {
-                    px[s] = 3.0e38f; py[s] = 0.0f; pz[s] = 0.0f; pid[s] = -1;
-                    if (SYMMETRIC) pr2[s] = -1.0f;
-                    if (s * 32 < T) {
-                        const int t = s * 32 + lane;
-                        if (t < T) {
-                            const int pos = candidate_pos(st, t);
-                            const float4 v = a.c_pts[pos];
-                            px[s] = v.x; py[s] = v.y; pz[s] = v.z; pid[s] = __float_as_int(v.w);
-                            if (SYMMETRIC) pr2[s] = a.c_r2[pos];
-                        }
-                    }
-                }
-                for (int q0 = qb; q0 < qe; q0 += 32) {
-                    const int qi = q0 + lane;
-                    float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    float qr2 = a.r2_fixed;
-                    if (qi < qe) {
-                        qv = a.q_pts[qi];
-                        if (VARIABLE) qr2 = a.q_r2[qi];
-                    }
-                    const int nq = min(32, qe - q0);
-                    for (int k = 0; k < nq; k++) {
-                        const int qidx = __float_as_int(__shfl_sync(kFull, qv.w, k));
-                        if (qidx >= a.query_limit) continue;
-                        const float qx = __shfl_sync(kFull, qv.x, k);
-                        const float qy = __shfl_sync(kFull, qv.y, k);
-                        const float qz = __shfl_sync(kFull, qv.z, k);
-                        const float r2 = VARIABLE ? __shfl_sync(kFull, qr2, k) : a.r2_fixed;
-                        uint32_t hits = 0;
+                for (int j = 0; j < NSLOT / 2; j++) {
+                    float x[2] = { 3.0e38f, 3.0e38f }, y[2] = { 0.0f, 0.0f }, z[2] = { 0.0f, 0.0f };
 #pragma unroll
-                        for (int s = 0; s < NSLOT; s++) {
-                            if (s * 32 < T) {
-                                const float d2 = dist2(qx, qy, qz, px[s], py[s], pz[s]);
-                                bool h = d2 <= r2;
-                                if (SYMMETRIC) h = h || (d2 <= pr2[s]);
-                                hits |= (h ? 1u : 0u) << s;
+                    for (int h = 0; h < 2; h++) {
+                        const int s = 2 * j + h;
+                        pid[s] = -1;
+                        if (SYMMETRIC) pr2[s] = -1.0f;
+                        if (s * 32 < T) {
+                            const int t = s * 32 + lane;
+                            if (t < T) {
+                                const int pos = candidate_pos(st, t);
+                                const float4 v = a.c_pts[pos];
+                                x[h] = v.x; y[h] = v.y; z[h] = v.z; pid[s] = __float_as_int(v.w);
+                                if (SYMMETRIC) pr2[s] = a.c_r2[pos];
                             }
                         }
-                        if (a.same_set) {
-                            const int ts = self_pre + (q0 + k - qb);
-                            if (lane == (ts & 31)) hits &= ~(1u << (ts >> 5));
+                    }
+                    px[j] = settle2(pack2(x[0], x[1])); py[j] = settle2(pack2(y[0], y[1])); pz[j] = settle2(pack2(z[0], z[1]));
+                }
+                // number of packed slot pairs in use; the query loop is instantiated per count so that its body is straight-line
+                const int npairs = (T + 63) >> 6;
+                auto run_queries = [&](auto np_tag) {
+                    constexpr int NP = decltype(np_tag)::value;
+                    for (int q0 = qb; q0 < qe; q0 += 32) {
+                        const int qi = q0 + lane;
+                        __syncwarp();
+                        if (qi < qe) {
+                            qbuf[lane] = a.q_pts[qi];
+                            if (VARIABLE) qr2s[lane] = a.q_r2[qi];
                         }
-                        const int cnt = __popc(hits);
-                        const int cinc = warp_inclusive_scan(cnt, lane);
-                        const int n = __shfl_sync(kFull, cinc, 31);
-                        nb_sum += (unsigned long long)n;
-                        nb_lo = min(nb_lo, n);
-                        nb_hi = max(nb_hi, n);
-                        bool ok;
-                        int* dst = reserve_list(st, a, lane, qidx, n, ok);
-                        if (ok) {
-                            int p = 1 + cinc - cnt;
+                        __syncwarp();
+                        const int nq = min(32, qe - q0);
+                        for (int k = 0; k < nq; k++) {
+                            const float4 q = qbuf[k];
+                            const int qidx = __float_as_int(q.w);
+                            if (qidx >= query_limit) continue;
+                            const float r2 = VARIABLE ? qr2s[k] : r2_fixed;
+                            if (st.wpos + 1 + NP * 64 > kStageInts || st.nrec == kStageRecs) stage_flush(st, a, lane);
+                            int* dst = st.ints + st.wpos + 1;
+                            // candidate t = s*32 + lane is the query itself  <=>  s*32 == selfkey  (never true when selfkey < 0)
+                            const int selfkey = same_set ? self_pre + (q0 + k - qb) - lane : -1;
+                            const f32x2 qx = pack2(q.x, q.x), qy = pack2(q.y, q.y), qz = pack2(q.z, q.z);
+                            int n = 0;
 #pragma unroll
-                            for (int s = 0; s < NSLOT; s++) {
-                                if (s * 32 < T) {
-                                    if (hits & (1u << s)) dst[p++] = pid[s];
+                            for (int j = 0; j < NP; j++) {
+                                const f32x2 dx = sub2(qx, px[j]);
+                                const f32x2 dy = sub2(qy, py[j]);
+                                const f32x2 dz = sub2(qz, pz[j]);
+                                const f32x2 d2p = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+                                float d2[2];
+                                unpack2(d2p, d2[0], d2[1]);
+#pragma unroll
+                                for (int h = 0; h < 2; h++) {
+                                    const int s = 2 * j + h;
+                                    bool hit = d2[h] <= r2;
+                                    if (SYMMETRIC) hit = hit || (d2[h] <= pr2[s]);
+                                    hit = hit && (selfkey != s * 32);
+                                    const unsigned m = __ballot_sync(kFull, hit);
+                                    if (hit) dst[n + __popc(m & lt)] = pid[s];
+                                    n += __popc(m);
                                 }
                             }
+                            if (lane == 0) {
+                                dst[-1] = n;
+                                st.rec_idx[st.nrec] = qidx;
+                                st.rec_off[st.nrec] = st.wpos;
+                            }
+                            st.wpos += n + 1;
+                            st.nrec += 1;
+                            nb_sum += (unsigned long long)n;
+                            nb_lo = min(nb_lo, n);
+                            nb_hi = max(nb_hi, n);
                         }
                     }
+                };
+                if (NSLOT == 8) {
+                    switch (npairs) {
+                    case 0: case 1: run_queries(std::integral_constant<int, 1>{}); break;
+                    case 2: run_queries(std::integral_constant<int, 2>{}); break;
+                    case 3: run_queries(std::integral_constant<int, 3>{}); break;
+                    default: run_queries(std::integral_constant<int, 4>{}); break;
+                    }
+                } else {
+                    if (npairs <= 2) run_queries(std::integral_constant<int, (NSLOT >= 4 ? 2 : NSLOT / 2)>{});
+                    else if (npairs <= 4) run_queries(std::integral_constant<int, (NSLOT >= 8 ? 4 : NSLOT / 2)>{});
+                    else if (npairs <= 6) run_queries(std::integral_constant<int, (NSLOT >= 12 ? 6 : NSLOT / 2)>{});
+                    else run_queries(std::integral_constant<int, NSLOT / 2>{});
                 }
             } else {
                 // ---------------- general path (very dense neighbourhoods): two sweeps per query, candidates re-read through L1
@@ -308,7 +393,6 @@ __global__ void __launch_bounds__(kQueryThreads, 2) query_kernel(const QueryArgs
                     int* dst = reserve_list(st, a, lane, qidx, n, ok);
                     if (!ok) continue;
                     int p = 1;
-                    const unsigned lt = lanemask_lt();
                     for (int t0 = 0; t0 < T; t0 += 32) {
                         const int t = t0 + lane;
                         bool h = false;

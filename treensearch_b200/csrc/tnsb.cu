@@ -348,7 +348,7 @@ int query_pair(tnsb_context* c, int si, int sj, const GridParams& gp, PairCounte
     const bool symmetric = variable && c->symmetric;   // TreeNSearch.cpp:2431
     // register slots for the candidate list: 27 cells of average population
     const double avg_cell = cj.n_cells > 0 ? (double)cj.n / cj.n_cells : 0.0;
-    const int grid = 2 * c->n_sms;
+    const int grid = kQueryBlocksPerSM * c->n_sms;
     cudaError_t e;
     if (27.0 * avg_cell * 1.15 <= 256.0) e = launch_query<Key, 8>(a, variable, symmetric, grid, c->stream);
     else e = launch_query<Key, 16>(a, variable, symmetric, grid, c->stream);
