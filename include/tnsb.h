@@ -45,8 +45,10 @@ enum {
     TNSB_OPT_LIST_CAPACITY = 3,  /* initial capacity, in ints per searching point, of the ragged list buffer (default 48) */
     TNSB_OPT_QUERY_LIMIT = 4,    /* >= 0: in every set only points with index < value are searching points; the remaining
                                     points are find-only ("ghost"/halo points of a Z-slab shard).  -1 (default): all points search */
-    TNSB_OPT_SORT_LISTS = 5      /* 1: sort every neighbour list ascending on the device before it is handed out (the
+    TNSB_OPT_SORT_LISTS = 5,     /* 1: sort every neighbour list ascending on the device before it is handed out (the
                                     reference's lists are ascending); 0 (default): cell-traversal order */
+    TNSB_OPT_POINT_STRIDE = 6    /* floats between consecutive points of float32 sets: 3 (default, xyzxyz as in the reference) or
+                                    4 ((x, y, z, id) records as produced by tnsb_shard_partition; the 4th word is ignored) */
 };
 
 /* timings (milliseconds, CUDA events on the engine's stream) and sizes of the last tnsb_run() */
@@ -152,6 +154,20 @@ int tnsb_get_zsort_order(const tnsb_context* ctx, int set_i, const int32_t** new
 /* device-side apply_zsort for float32 arrays resident in HBM: data[new*stride + c] = tmp[old*stride + c]
    (host arrays of arbitrary T are gathered by the header template, TreeNSearch.h:443-481) */
 int tnsb_apply_zsort_device_f32(tnsb_context* ctx, int set_i, float* d_data, int stride);
+
+/* ---- multi-GPU: Z-slab decomposition helpers (no counterpart in the single-process reference) ---------------- */
+/* min/max of a device-resident chunk of points: out = {min x, y, z, max x, y, z}.  Synchronises the stream. */
+int tnsb_shard_aabb(tnsb_context* ctx, const float* d_points, int n_points, int stride, float out_min_max[6]);
+/* histogram (n_bins <= 8192 uint32 bins over [lo, hi)) of one coordinate of a device-resident chunk; asynchronous on the stream.
+   All-reduced over the ranks it yields slab cuts with equal point counts. */
+int tnsb_shard_histogram(tnsb_context* ctx, const float* d_points, int n_points, int stride, int axis, float lo, float hi,
+                         int n_bins, uint32_t* d_hist);
+/* Buckets a device-resident chunk into (x, y, z, bits(id_base + i)) float4 records ordered
+       [owned by part 0 | ... | owned by part P-1 | halo of part 0 | ... | halo of part P-1]
+   part g owns coordinates in [cuts[g], cuts[g+1]) (cuts[0] / cuts[P] are ignored: -inf / +inf) and gets as halo every other
+   point within `halo` of that interval.  counts_out[0..P) = owned counts, counts_out[P..2P) = halo counts.  Synchronises. */
+int tnsb_shard_partition(tnsb_context* ctx, const float* d_points, int n_points, int stride, int id_base, int axis,
+                         const float* cuts, int n_parts, float halo, float* d_records, int64_t capacity_records, int64_t* counts_out);
 
 /* ---- diagnostics ---------------------------------------------------------------------------------------------------- */
 /* replaces: get_neighborlist_n_bytes()  TreeNSearch.h:246 / .cpp:254-261 */

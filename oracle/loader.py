@@ -34,6 +34,14 @@ def build(quiet: bool = True) -> None:
                    stdout=subprocess.DEVNULL if quiet else None)
 
 
+REF_TESTS_BIN = os.path.join(_HERE, "_ref", "ref_tests_on_b200")
+
+
+def build_ref_tests(quiet: bool = True) -> None:
+    """Compile the reference's own tests against include/TreeNSearch + libtnsb.so (needs /root/reference and a built library)."""
+    subprocess.run(["make", "-C", _HERE, "ref-tests"], check=True, stdout=subprocess.DEVNULL if quiet else None)
+
+
 def _f32(a):
     if a is None:
         return None

@@ -1,0 +1,49 @@
+"""Worker of the multi-GPU parity test: python -m torch.distributed.run --nproc-per-node N tests/sharded_worker.py
+Every rank searches its Z-slab with the CUDA engine; lists (translated to global ids) must equal the restated oracle's
+lists on the whole cloud."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT)
+
+from oracle import loader  # noqa: E402
+from treensearch_b200 import clouds, sharded  # noqa: E402
+
+
+def main():
+    rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_total = 200_000
+    cloud = clouds.uniform_cloud(n_total, 77)
+    cloud[:, 2] = cloud[:, 2] ** 1.5
+    r = float(clouds.radius_for_mean_neighbors(n_total, 25.0))
+    per = n_total // world
+    chunk = torch.from_numpy(np.ascontiguousarray(cloud[rank * per:(rank + 1) * per])).cuda()
+    search = sharded.ShardedSearch(r, rank, world, local_rank, stream=torch.cuda.current_stream(), dist=dist)
+    for _ in range(2):                                   # second step reuses buffers (resize path)
+        search.step(chunk, rank * per)
+    mine = search.owned_lists_global()
+    port = loader.OraclePort()
+    port.set_search_radius(r)
+    port.add_point_set(cloud)
+    port.set_active_search(0, 0, True)
+    port.run(1)
+    off, idx = port.csr(0, 0)
+    for g, lst in mine.items():
+        assert np.array_equal(lst, idx[off[g]:off[g + 1]]), f"rank {rank}: global point {g} differs"
+    counts = torch.tensor([len(mine)], device="cuda")
+    dist.all_reduce(counts)
+    assert int(counts.item()) == n_total, "owned points do not partition the cloud"
+    if rank == 0:
+        print(f"SHARDED_OK world={world} owned={len(mine)} halo={search.n_halo}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -23,6 +23,7 @@ TNSB_OPT_PIN_USER_MEMORY = 2
 TNSB_OPT_LIST_CAPACITY = 3
 TNSB_OPT_QUERY_LIMIT = 4
 TNSB_OPT_SORT_LISTS = 5
+TNSB_OPT_POINT_STRIDE = 6
 
 
 class Stats(C.Structure):
@@ -78,6 +79,10 @@ SIGNATURES = {
     "tnsb_prepare_zsort": (C.c_int, [_vp]),
     "tnsb_get_zsort_order": (C.c_int, [_vp, C.c_int, _i32pp, C.POINTER(C.c_int)]),
     "tnsb_apply_zsort_device_f32": (C.c_int, [_vp, C.c_int, _vp, C.c_int]),
+    "tnsb_shard_aabb": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "tnsb_shard_histogram": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, _vp]),
+    "tnsb_shard_partition": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_float, _vp, C.c_int64,
+                                       C.POINTER(C.c_int64)]),
     "tnsb_get_neighborlist_n_bytes": (C.c_uint64, [_vp]),
     "tnsb_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "tnsb_get_pair_neighbor_stats": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_int64)]),

@@ -20,21 +20,20 @@ template <> __device__ __forceinline__ float to_f32<double>(double v) { return _
 
 constexpr int kAabbThreads = 256;
 
+// `stride` = elements between consecutive points of the input (3 for xyzxyz, 4 for (x,y,z,id) records); the float
+// conversion output is always packed xyz.
 template <typename T>
-__global__ void __launch_bounds__(kAabbThreads) aabb_kernel(const T* __restrict__ pts, const T* __restrict__ radii, int n,
+__global__ void __launch_bounds__(kAabbThreads) aabb_kernel(const T* __restrict__ pts, const T* __restrict__ radii, int n, int stride,
                                                             float* __restrict__ pts_f32_out, float* __restrict__ radii_f32_out,
                                                             uint32_t* __restrict__ out)
 {
     float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
     float rlo = INFINITY, rhi = -INFINITY;
-    // flat walk over the 3n coordinates: fully coalesced, component = flat index mod 3
-    const int64_t total = 3ll * n;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 3;
-    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 3; base < total; base += stride) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            const float v = to_f32<T>(pts[base + c]);
-            if (pts_f32_out) pts_f32_out[base + c] = v;
+            const float v = to_f32<T>(pts[i * stride + c]);
+            if (pts_f32_out) pts_f32_out[i * 3 + c] = v;
             lo[c] = fminf(lo[c], v);
             hi[c] = fmaxf(hi[c], v);
         }
@@ -73,11 +72,12 @@ __global__ void __launch_bounds__(kAabbThreads) aabb_kernel(const T* __restrict_
 // ----------------------------------------------------------------------------------------------------------------------
 // Cell assignment + Morton key.  ijk = floor((p - bottom) * inv_cell) like TreeNSearch.cpp:713-715, but in fp64 and clamped.
 template <typename Key>
-__global__ void __launch_bounds__(256) keygen_kernel(const float* __restrict__ pts, int n, GridParams g, Key* __restrict__ keys)
+__global__ void __launch_bounds__(256) keygen_kernel(const float* __restrict__ pts, int n, int stride, GridParams g, Key* __restrict__ keys)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float x = pts[3ll * i], y = pts[3ll * i + 1], z = pts[3ll * i + 2];
+    const float* p = pts + (int64_t)i * stride;
+    const float x = p[0], y = p[1], z = p[2];
     int cx = __double2int_rd(((double)x - g.bottom[0]) * g.inv_cell);
     int cy = __double2int_rd(((double)y - g.bottom[1]) * g.inv_cell);
     int cz = __double2int_rd(((double)z - g.bottom[2]) * g.inv_cell);
@@ -90,13 +90,13 @@ __global__ void __launch_bounds__(256) keygen_kernel(const float* __restrict__ p
 // ----------------------------------------------------------------------------------------------------------------------
 // Reorder: sorted[i] = (x, y, z, bits(idx)) of the point that the sort put at position i; r2[i] = r*r (float, like
 // TreeNSearch.cpp:2352) in variable radius mode.  ids[] (optional) replaces the set-local index by a caller supplied id.
-__global__ void __launch_bounds__(256) reorder_kernel(const float* __restrict__ pts, const float* __restrict__ radii, const uint32_t* __restrict__ order,
+__global__ void __launch_bounds__(256) reorder_kernel(const float* __restrict__ pts, int stride, const float* __restrict__ radii, const uint32_t* __restrict__ order,
                                                       int n, float4* __restrict__ sorted, float* __restrict__ sorted_r2)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t src = order[i];
-    const float* p = pts + 3ll * src;
+    const float* p = pts + (int64_t)src * stride;
     sorted[i] = make_float4(p[0], p[1], p[2], __uint_as_float(src));
     if (radii) {
         const float r = radii[src];

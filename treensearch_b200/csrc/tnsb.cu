@@ -11,6 +11,7 @@
 #include "radix_sort.cuh"
 #include "grid_build.cuh"
 #include "query.cuh"
+#include "shard.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -84,6 +85,7 @@ struct SetState {
     DevBuf cv_pts, cv_radii;       // float conversions of double arrays
     const float* d_pts = nullptr;  // float xyz actually used by the kernels
     const float* d_radii = nullptr;
+    int d_stride = 3;              // floats between consecutive points of d_pts
     DevBuf keys[2], vals[2];
     int sel = 0;
     DevBuf sorted, sorted_r2;
@@ -136,6 +138,7 @@ struct tnsb_context {
     int64_t opt_list_capacity = 48;
     int64_t opt_query_limit = -1;
     bool opt_sort_lists = false;
+    int opt_point_stride = 3;
 
     // world box with hysteresis (TreeNSearch.cpp:474-482)
     bool domain_valid = false;
@@ -232,7 +235,7 @@ int build_sets(tnsb_context* c, const GridParams& gp)
             TNSB_CUDA(c, st.keys[b].ensure(sizeof(Key) * (size_t)st.n, 1.1));
             TNSB_CUDA(c, st.vals[b].ensure(sizeof(uint32_t) * (size_t)st.n, 1.1));
         }
-        keygen_kernel<Key><<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.n, gp, st.keys[0].as<Key>());
+        keygen_kernel<Key><<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.n, st.d_stride, gp, st.keys[0].as<Key>());
         launches++;
     }
     TNSB_CUDA(c, cudaEventRecord(c->ev[EV_KEYS], s));
@@ -252,7 +255,7 @@ int build_sets(tnsb_context* c, const GridParams& gp)
         if (st.n == 0) continue;
         TNSB_CUDA(c, st.sorted.ensure(sizeof(float4) * (size_t)st.n, 1.1));
         if (st.has_radii) TNSB_CUDA(c, st.sorted_r2.ensure(sizeof(float) * (size_t)st.n, 1.1));
-        reorder_kernel<<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.has_radii ? st.d_radii : nullptr, st.vals[st.sel].as<uint32_t>(), st.n,
+        reorder_kernel<<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.d_stride, st.has_radii ? st.d_radii : nullptr, st.vals[st.sel].as<uint32_t>(), st.n,
                                                           st.sorted.as<float4>(), st.sorted_r2.as<float>());
         launches++;
     }
@@ -379,11 +382,12 @@ int build_grid(tnsb_context* c, GridParams* gp_out)
         auto& st = c->sets[si];
         st.sorted_valid = false;
         const size_t esz = st.is_f64 ? 8 : 4;
+        const size_t stride = st.is_f64 ? 3 : (size_t)c->opt_point_stride;
         const void* up = st.is_f64 ? (const void*)st.u_pts_f64 : (const void*)st.u_pts_f32;
         const void* ur = st.is_f64 ? (const void*)st.u_radii_f64 : (const void*)st.u_radii_f32;
         if (st.n > 0 && !up) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: point set " + std::to_string(si) + " has a null coordinate pointer.");
         if (st.n > 0 && st.has_radii && !ur) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: point set " + std::to_string(si) + " has a null radii pointer.");
-        int rc = stage_input(c, up, esz * 3 * (size_t)st.n, st.up_pts, &raw_pts[si]);
+        int rc = stage_input(c, up, esz * stride * (size_t)st.n, st.up_pts, &raw_pts[si]);
         if (rc != TNSB_OK) return rc;
         rc = stage_input(c, st.has_radii ? ur : nullptr, esz * (size_t)st.n, st.up_radii, &raw_radii[si]);
         if (rc != TNSB_OK) return rc;
@@ -401,14 +405,16 @@ int build_grid(tnsb_context* c, GridParams* gp_out)
         if (st.is_f64) {
             TNSB_CUDA(c, st.cv_pts.ensure(sizeof(float) * 3 * (size_t)st.n, 1.1));
             if (st.has_radii) TNSB_CUDA(c, st.cv_radii.ensure(sizeof(float) * (size_t)st.n, 1.1));
-            aabb_kernel<double><<<aabb_grid, kAabbThreads, 0, s>>>((const double*)raw_pts[si], st.has_radii ? (const double*)raw_radii[si] : nullptr, st.n,
+            aabb_kernel<double><<<aabb_grid, kAabbThreads, 0, s>>>((const double*)raw_pts[si], st.has_radii ? (const double*)raw_radii[si] : nullptr, st.n, 3,
                                                                   st.cv_pts.as<float>(), st.has_radii ? st.cv_radii.as<float>() : nullptr, c->d_reduce.as<uint32_t>());
             st.d_pts = st.cv_pts.as<float>();
+            st.d_stride = 3;
             st.d_radii = st.has_radii ? st.cv_radii.as<float>() : nullptr;
         } else {
-            aabb_kernel<float><<<aabb_grid, kAabbThreads, 0, s>>>((const float*)raw_pts[si], st.has_radii ? (const float*)raw_radii[si] : nullptr, st.n, nullptr, nullptr,
-                                                                 c->d_reduce.as<uint32_t>());
+            aabb_kernel<float><<<aabb_grid, kAabbThreads, 0, s>>>((const float*)raw_pts[si], st.has_radii ? (const float*)raw_radii[si] : nullptr, st.n,
+                                                                 c->opt_point_stride, nullptr, nullptr, c->d_reduce.as<uint32_t>());
             st.d_pts = (const float*)raw_pts[si];
+            st.d_stride = c->opt_point_stride;
             st.d_radii = st.has_radii ? (const float*)raw_radii[si] : nullptr;
         }
         c->stats.n_kernel_launches++;
@@ -815,6 +821,9 @@ int tnsb_set_option(tnsb_context* c, int option, int64_t value)
         c->opt_list_capacity = value; return TNSB_OK;
     case TNSB_OPT_QUERY_LIMIT: c->opt_query_limit = value; return TNSB_OK;
     case TNSB_OPT_SORT_LISTS: c->opt_sort_lists = value != 0; return TNSB_OK;
+    case TNSB_OPT_POINT_STRIDE:
+        if (value != 3 && value != 4) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: point stride must be 3 (xyz) or 4 (xyz + id).");
+        c->opt_point_stride = (int)value; return TNSB_OK;
     default: return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: unknown option.");
     }
 }
@@ -940,6 +949,71 @@ int tnsb_apply_zsort_device_f32(tnsb_context* c, int s, float* d_data, int strid
     TNSB_CUDA(c, cudaMemcpyAsync(c->scan_temp.p, d_data, bytes, cudaMemcpyDeviceToDevice, c->stream));
     const int64_t total = (int64_t)st.n * stride;
     gather_rows_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, c->stream>>>(c->scan_temp.as<float>(), d_data, st.d_zorder.as<int32_t>(), st.n, stride);
+    TNSB_CUDA(c, cudaGetLastError());
+    TNSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TNSB_OK;
+}
+
+// ---- multi-GPU (Z-slab) helpers -------------------------------------------------------------------------------------------
+int tnsb_shard_aabb(tnsb_context* c, const float* d_points, int n, int stride, float out_min_max[6])
+{
+    if (!c || !out_min_max || (stride != 3 && stride != 4)) return TNSB_ERR_INVALID_ARGUMENT;
+    TNSB_CUDA(c, cudaSetDevice(c->device));
+    TNSB_CUDA(c, c->h_small.ensure(4096));
+    TNSB_CUDA(c, c->d_reduce.ensure(64));
+    uint32_t* h_red = c->h_small.as<uint32_t>();
+    for (int k = 0; k < 8; k++) h_red[k] = ((k < 3) || (k == 6)) ? 0xffffffffu : 0u;
+    TNSB_CUDA(c, cudaMemcpyAsync(c->d_reduce.p, h_red, 32, cudaMemcpyHostToDevice, c->stream));
+    if (n > 0) {
+        if (!is_device_pointer(d_points)) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb_shard_aabb: points must be device memory.");
+        aabb_kernel<float><<<4 * c->n_sms, kAabbThreads, 0, c->stream>>>(d_points, nullptr, n, stride, nullptr, nullptr, c->d_reduce.as<uint32_t>());
+    }
+    TNSB_CUDA(c, cudaMemcpyAsync(h_red + 8, c->d_reduce.p, 32, cudaMemcpyDeviceToHost, c->stream));
+    TNSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int d = 0; d < 6; d++) out_min_max[d] = ordered_to_float(h_red[8 + d]);
+    return TNSB_OK;
+}
+
+int tnsb_shard_histogram(tnsb_context* c, const float* d_points, int n, int stride, int axis, float lo, float hi, int n_bins, uint32_t* d_hist)
+{
+    if (!c || !d_hist || axis < 0 || axis > 2 || n_bins < 1 || n_bins > 8192 || (stride != 3 && stride != 4)) return TNSB_ERR_INVALID_ARGUMENT;
+    TNSB_CUDA(c, cudaSetDevice(c->device));
+    TNSB_CUDA(c, cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * (size_t)n_bins, c->stream));
+    if (n > 0) {
+        const float inv_bin = hi > lo ? (float)n_bins / (hi - lo) : 0.0f;
+        axis_histogram_kernel<<<2 * c->n_sms, kShardThreads, sizeof(uint32_t) * (size_t)n_bins, c->stream>>>(d_points, n, stride, axis, lo, inv_bin, n_bins, d_hist);
+        TNSB_CUDA(c, cudaGetLastError());
+    }
+    return TNSB_OK;
+}
+
+int tnsb_shard_partition(tnsb_context* c, const float* d_points, int n, int stride, int id_base, int axis, const float* cuts, int n_parts, float halo,
+                         float* d_records, int64_t capacity_records, int64_t* counts_out)
+{
+    if (!c || !cuts || !counts_out || axis < 0 || axis > 2 || n_parts < 1 || n_parts > kMaxParts || (stride != 3 && stride != 4)) return TNSB_ERR_INVALID_ARGUMENT;
+    TNSB_CUDA(c, cudaSetDevice(c->device));
+    SlabCuts sc;
+    sc.n_parts = n_parts;
+    sc.halo = halo;
+    for (int k = 0; k <= n_parts; k++) sc.cut[k] = cuts[k];
+    const size_t nb = 2 * (size_t)n_parts;
+    TNSB_CUDA(c, c->d_misc.ensure(sizeof(unsigned long long) * 2 * nb + 1024));
+    TNSB_CUDA(c, c->h_small.ensure(4096 + sizeof(unsigned long long) * 2 * nb));
+    unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(c->d_misc.as<char>() + 512);
+    unsigned long long* d_cursors = d_counts + nb;
+    unsigned long long* h_counts = reinterpret_cast<unsigned long long*>(c->h_small.as<char>() + 1024);
+    TNSB_CUDA(c, cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * nb, c->stream));
+    const int grid = 4 * c->n_sms;
+    if (n > 0) slab_count_kernel<<<grid, kShardThreads, 0, c->stream>>>(d_points, n, stride, axis, sc, d_counts);
+    TNSB_CUDA(c, cudaMemcpyAsync(h_counts, d_counts, sizeof(unsigned long long) * nb, cudaMemcpyDeviceToHost, c->stream));
+    TNSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    unsigned long long total = 0;
+    unsigned long long* h_prefix = h_counts + nb;
+    for (size_t b = 0; b < nb; b++) { counts_out[b] = (int64_t)h_counts[b]; h_prefix[b] = total; total += h_counts[b]; }
+    if ((int64_t)total > capacity_records)
+        return fail(c, TNSB_ERR_LIMIT, "tnsb_shard_partition: record buffer too small (" + std::to_string(total) + " records needed).");
+    TNSB_CUDA(c, cudaMemcpyAsync(d_cursors, h_prefix, sizeof(unsigned long long) * nb, cudaMemcpyHostToDevice, c->stream));
+    if (n > 0) slab_scatter_kernel<<<grid, kShardThreads, 0, c->stream>>>(d_points, n, stride, axis, id_base, sc, d_cursors, reinterpret_cast<float4*>(d_records));
     TNSB_CUDA(c, cudaGetLastError());
     TNSB_CUDA(c, cudaStreamSynchronize(c->stream));
     return TNSB_OK;

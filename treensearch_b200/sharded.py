@@ -1,0 +1,211 @@
+"""Multi-GPU path: Z-slab sharding of one point cloud across the GPUs of a box, one process per GPU.
+
+The reference is a single shared-memory process; this decomposition is new design.  Per step and per rank:
+
+  1. world box of the local chunk (CUDA reduction)                       -> all_reduce(MAX) of [-min, max]      (24 bytes)
+  2. histogram of the slab axis over the world extent (CUDA kernel)      -> all_reduce(SUM)                     (16 KB)
+     -> the same balanced cuts on every rank (equal point counts per slab)
+  3. bucket partition of the local chunk into (x, y, z, global id) records, ordered
+        [owned by rank 0 | ... | owned by rank G-1 | halo of rank 0 | ... | halo of rank G-1]   (two CUDA kernels)
+  4. ONE exchange step: all_to_all of the per-destination counts, then all_to_all_single of the owned records and of
+     the halo records (NCCL over NVLink / NVSwitch).  A halo of width >= r_max on both sides is all a fixed-radius
+     query needs, so there is no second exchange.
+  5. the single-GPU engine on [owned | halo] records with TNSB_OPT_QUERY_LIMIT = n_owned: halo points are find-only.
+
+Neighbour lists come back in LOCAL indices (into the rank's [owned | halo] array, which is what a distributed consumer
+indexes anyway); `local_ids` maps them to global point ids.  No data-path collective other than step 4 exists.
+
+The host logic (cuts, count bookkeeping, exchange) is backend agnostic and is exercised on CPU with gloo in
+tests/test_sharded_cpu.py; the partition / search themselves need the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+def balanced_cuts(hist: np.ndarray, lo: float, hi: float, n_parts: int) -> np.ndarray:
+    """Cut coordinates (float32, length n_parts + 1) such that every part holds ~ the same number of points.
+    hist: global histogram over n_bins equal bins of [lo, hi).  cuts[0] = -inf, cuts[-1] = +inf; inner cuts lie on bin edges."""
+    hist = np.asarray(hist, dtype=np.int64)
+    n_bins = hist.shape[0]
+    total = int(hist.sum())
+    cum = np.cumsum(hist)
+    cuts = np.empty(n_parts + 1, dtype=np.float32)
+    cuts[0], cuts[-1] = -np.inf, np.inf
+    width = (float(hi) - float(lo)) / n_bins
+    prev = 0
+    for g in range(1, n_parts):
+        target = (total * g) // n_parts
+        b = int(np.searchsorted(cum, target, side="left")) + 1      # cut after the bin that reaches the target
+        b = min(max(b, prev), n_bins)
+        prev = b
+        cuts[g] = np.float32(float(lo) + b * width)
+    return cuts
+
+
+def halo_width(r_max: float) -> np.float32:
+    """Halo strictly wider than any search distance (float rounding of d2 / r^2 included)."""
+    return np.float32(np.float32(r_max) * np.float32(1.0 + 1.0 / 1024.0))
+
+
+def exchange_records(dist, records, counts: np.ndarray, world: int):
+    """Step 4.  `records` is a torch tensor [total, 4] laid out as the partition produced it; counts = int64[2*world]
+    (owned counts then halo counts, per destination).  Returns (local [n_owned + n_halo, 4], n_owned, n_halo)."""
+    import torch
+    dev = records.device
+    send_counts = torch.from_numpy(np.ascontiguousarray(counts.reshape(2, world).T)).to(dev)     # [dest, kind]
+    recv_counts = torch.empty_like(send_counts)
+    if world > 1:
+        dist.all_to_all_single(recv_counts, send_counts)
+    else:
+        recv_counts.copy_(send_counts)
+    rc = recv_counts.cpu().numpy()                      # [source, kind]
+    own_in, halo_in = rc[:, 0].astype(np.int64), rc[:, 1].astype(np.int64)
+    own_out, halo_out = counts[:world].astype(np.int64), counts[world:].astype(np.int64)
+    n_owned, n_halo = int(own_in.sum()), int(halo_in.sum())
+    local = torch.empty((n_owned + n_halo, 4), dtype=records.dtype, device=dev)
+    owned_src = records[: int(own_out.sum())]
+    halo_src = records[int(own_out.sum()): int(own_out.sum() + halo_out.sum())]
+    if world > 1:
+        dist.all_to_all_single(local[:n_owned], owned_src, output_split_sizes=own_in.tolist(), input_split_sizes=own_out.tolist())
+        dist.all_to_all_single(local[n_owned:], halo_src, output_split_sizes=halo_in.tolist(), input_split_sizes=halo_out.tolist())
+    else:
+        local[:n_owned].copy_(owned_src)
+        local[n_owned:].copy_(halo_src)
+    return local, n_owned, n_halo
+
+
+class ShardedSearch:
+    """One rank of the Z-slab sharded fixed-radius search.  `dist` is torch.distributed (already initialised) or None."""
+
+    def __init__(self, radius: float, rank: int = 0, world: int = 1, device: int = 0, axis: int = 2, n_bins: int = 4096,
+                 stream=None, dist=None):
+        import torch
+        from .api import TreeNSearch
+        self.torch = torch
+        self.dist = dist
+        self.rank, self.world, self.axis, self.n_bins = rank, world, axis, n_bins
+        self.radius = float(np.float32(radius))
+        self.device = torch.device("cuda", device)
+        self.engine = TreeNSearch(device)
+        if stream is not None:
+            self.engine.set_stream(stream.cuda_stream)
+        self.engine.set_search_radius(self.radius)
+        self.engine.set_option(L.TNSB_OPT_POINT_STRIDE, 4)
+        self._set_added = False
+        self._hist = torch.zeros(n_bins, dtype=torch.int32, device=self.device)
+        self._records = None
+        self.local = None
+        self.n_owned = self.n_halo = 0
+        self.cuts = None
+
+    # ---- thin wrappers of the shard helpers of the C ABI
+    def _aabb(self, pts):
+        out = (C.c_float * 6)()
+        self.engine._check(self.engine._lib.tnsb_shard_aabb(self.engine._h, pts.data_ptr(), pts.shape[0], pts.shape[1], out))
+        return np.array(out[:], dtype=np.float32)
+
+    def _histogram(self, pts, lo, hi):
+        self.engine._check(self.engine._lib.tnsb_shard_histogram(self.engine._h, pts.data_ptr(), pts.shape[0], pts.shape[1], self.axis,
+                                                                float(lo), float(hi), self.n_bins, self._hist.data_ptr()))
+
+    def _partition(self, pts, id_base, cuts, halo):
+        torch = self.torch
+        need = int(pts.shape[0] * 1.3) + 1024
+        if self._records is None or self._records.shape[0] < need:
+            self._records = torch.empty((need, 4), dtype=torch.float32, device=self.device)
+        counts = (C.c_int64 * (2 * self.world))()
+        cuts_c = (C.c_float * (self.world + 1))(*[float(c) if np.isfinite(c) else 0.0 for c in cuts])
+        self.engine._check(self.engine._lib.tnsb_shard_partition(self.engine._h, pts.data_ptr(), pts.shape[0], pts.shape[1], int(id_base), self.axis,
+                                                                cuts_c, self.world, float(halo), self._records.data_ptr(), self._records.shape[0], counts))
+        return np.array(counts[:], dtype=np.int64)
+
+    def step(self, points, id_base: int):
+        """points: float32 CUDA tensor [n_local, 3] (this rank's chunk of the global cloud, ids id_base .. id_base + n_local)."""
+        torch, dist = self.torch, self.dist
+        # 1. world box
+        mm = self._aabb(points)
+        box = torch.from_numpy(np.concatenate([-mm[:3], mm[3:]])).to(self.device)
+        if self.world > 1:
+            dist.all_reduce(box, op=dist.ReduceOp.MAX)
+        box = box.cpu().numpy()
+        lo, hi = -box[self.axis], box[3 + self.axis]
+        hi = hi + max(1e-6 * abs(hi - lo), 1e-30)
+        # 2. balanced cuts
+        self._histogram(points, lo, hi)
+        if self.world > 1:
+            dist.all_reduce(self._hist, op=dist.ReduceOp.SUM)
+        self.cuts = balanced_cuts(self._hist.cpu().numpy(), lo, hi, self.world)
+        # 3. partition, 4. exchange
+        counts = self._partition(points, id_base, self.cuts, halo_width(self.radius))
+        self.local, self.n_owned, self.n_halo = exchange_records(dist, self._records, counts, self.world)
+        # 5. local search, halo points find-only
+        eng = self.engine
+        eng.set_option(L.TNSB_OPT_QUERY_LIMIT, self.n_owned)
+        if not self._set_added:
+            eng.add_point_set(self.local, n_points=self.local.shape[0])
+            eng.set_active_search(0, 0, True)
+            self._set_added = True
+        else:
+            eng.resize_point_set(0, self.local, n_points=self.local.shape[0])
+        eng.run()
+
+    # ---- results
+    def local_ids(self) -> np.ndarray:
+        """Global id of every local point ([owned | halo] order)."""
+        return self.local[:, 3].contiguous().view(self.torch.int32).cpu().numpy()
+
+    def owned_lists_global(self):
+        """{global id of owned point: sorted array of global neighbour ids} -- test helper, small inputs only."""
+        ids = self.local_ids()
+        ragged, pos = self.engine.neighbor_lists(0, 0)
+        out = {}
+        for i in range(self.n_owned):
+            p = int(pos[i])
+            n = int(ragged[p])
+            out[int(ids[i])] = np.sort(ids[ragged[p + 1: p + 1 + n]])
+        return out
+
+
+class ShardedUniformJob:
+    """bench.py helper: this rank's 1/world chunk of a synthetic cloud, stepped device-resident or end-to-end."""
+
+    def __init__(self, workload, points_per_gpu, rank, world, local_rank, stream):
+        import torch
+        import torch.distributed as dist
+        from . import clouds
+        total = points_per_gpu * world
+        if workload != "uniform":
+            raise SystemExit("multi-GPU bench supports the uniform workload")
+        self.radius = float(clouds.radius_for_mean_neighbors(total))
+        chunk = clouds.uniform_cloud(points_per_gpu, 42 + rank)          # i.i.d. uniform chunk of the global cloud
+        self.h_pts = torch.from_numpy(chunk).pin_memory()
+        self.d_pts = self.h_pts.cuda(non_blocking=False)
+        self.d_stage = torch.empty_like(self.d_pts)
+        self.id_base = rank * points_per_gpu
+        self.search = ShardedSearch(self.radius, rank, world, local_rank, stream=stream, dist=dist if world > 1 else None)
+        self._stats = None
+        self._stats_e2e = None
+
+    def step_device(self):
+        self.search.engine.set_option(L.TNSB_OPT_HOST_RESULTS, 0)
+        self.search.step(self.d_pts, self.id_base)
+        self._stats = self.search.engine.stats()
+
+    def step_e2e(self):
+        self.search.engine.set_option(L.TNSB_OPT_HOST_RESULTS, 1)
+        self.d_stage.copy_(self.h_pts, non_blocking=True)               # host -> device of this step's inputs
+        self.search.step(self.d_stage, self.id_base)
+        st = self.search.engine.stats()
+        st["h2d_bytes"] = int(self.h_pts.numel() * 4)
+        self._stats_e2e = st
+
+    def stats(self):
+        return self._stats
+
+    def stats_e2e(self):
+        return self._stats_e2e
