@@ -120,8 +120,9 @@ int tnsb_set_active_search_of_set(tnsb_context* ctx, int set_i, int search_neigh
 int tnsb_set_all_searches(tnsb_context* ctx, int active);
 /* engine options (TNSB_OPT_*) */
 int tnsb_set_option(tnsb_context* ctx, int option, int64_t value);
-/* run every kernel and copy of this context on the caller's CUDA stream (a cudaStream_t passed as void*; NULL restores the
-   context's own non-blocking stream).  Lets a host framework order the search against its own work and time it with its own events. */
+/* run every kernel and copy of this context on the caller's CUDA stream (a cudaStream_t passed as void*; NULL is the legacy
+   default stream, (void*)-1 restores the context's own non-blocking stream).  Lets a host framework order the search against
+   its own work (e.g. NCCL collectives that produced the points) and time it with its own events. */
 int tnsb_set_stream(tnsb_context* ctx, void* cuda_stream);
 
 /* ---- getters (TreeNSearch.h:304-334 / .cpp:191-220) --------------------------------------------------------------- */

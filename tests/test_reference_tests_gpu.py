@@ -19,5 +19,6 @@ def test_reference_test_program_passes_on_the_cuda_engine(built_library):
     out = res.stdout
     assert res.returncode == 0, out[-3000:] + res.stderr[-2000:]
     assert "FAILED" not in out, out[-3000:]
-    assert out.count("passed!") >= 3 * (9 + 9 + 9 + 3), out[-3000:]
+    # per size: 3 cases x 7 'passed!' lines (tests/tests.cpp:34-89) + 3 lines of resize_variable_radius (:188-237)
+    assert out.count("passed!") == 3 * (3 * 7 + 3), out[-3000:]
     assert "Runtime parallel SIMD" in out

@@ -279,8 +279,10 @@ class TreeNSearch:
             self._query_limit = int(value)
 
     def set_stream(self, cuda_stream):
-        """Run on the caller's CUDA stream (an int cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream); 0/None = own stream."""
-        self._check(self._lib.tnsb_set_stream(self._h, C.c_void_p(int(cuda_stream) if cuda_stream else None)))
+        """Run on the caller's CUDA stream (an int cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream; 0 is the legacy
+        default stream).  None restores the context's own stream."""
+        handle = C.c_void_p(-1) if cuda_stream is None else C.c_void_p(int(cuda_stream))
+        self._check(self._lib.tnsb_set_stream(self._h, handle))
 
     def stats(self) -> dict:
         st = L.Stats()

@@ -832,7 +832,7 @@ int tnsb_set_stream(tnsb_context* c, void* cuda_stream)
 {
     if (!c) return TNSB_ERR_INVALID_ARGUMENT;
     cudaStreamSynchronize(c->stream);
-    c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    c->stream = (cuda_stream == reinterpret_cast<void*>(-1)) ? c->own_stream : static_cast<cudaStream_t>(cuda_stream);
     return TNSB_OK;
 }
 
