@@ -307,7 +307,7 @@ def test_device_resident_io(tnsb):
     with pytest.raises(tnsb.TreeNSearchError):
         eng.neighbor_lists(0, 0)
     d_ragged, d_pos, n_ints = eng.neighbor_lists_device(0, 0)
-    assert n_ints == st["n_list_ints"] == st["n_neighbors"] + 5000
+    assert n_ints == st["n_list_ints"] >= st["n_neighbors"] + 5000      # + alignment padding between flushes
     # pinned host input takes the same path as pageable input
     pinned = torch.from_numpy(case["sets"][0][0]).pin_memory()
     eng2 = tnsb.TreeNSearch()

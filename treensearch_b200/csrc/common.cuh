@@ -90,6 +90,62 @@ template <> struct Morton<uint64_t> {
     }
 };
 
+// ---- neighbour cell in Morton space: +-1 per axis by dilated-integer arithmetic, no decode / encode round trip.
+// `valid` is cleared when the neighbour would leave [0, 2^bits) on some axis.
+template <typename Key> struct MortonMask;
+template <> struct MortonMask<uint32_t> { static constexpr uint32_t kX = 0x09249249u; };
+template <> struct MortonMask<uint64_t> { static constexpr uint64_t kX = 0x1249249249249249ull; };
+
+template <typename Key>
+__device__ __forceinline__ Key morton_neighbor(Key key, int ox, int oy, int oz, Key key_mask, bool& valid)
+{
+    Key out = 0;
+    const int o[3] = { ox, oy, oz };
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const Key md = (MortonMask<Key>::kX << d) & key_mask;     // bits of axis d that are in use
+        const Key part = key & md;
+        Key r = part;
+        if (o[d] > 0) { valid = valid && (part != md); r = ((key | ~md) + (Key)1) & md; }
+        if (o[d] < 0) { valid = valid && (part != 0); r = (part - (Key)1) & md; }
+        out |= r;
+    }
+    return out;
+}
+
+// ---- open addressing hash  cell key -> compact cell id.  One slot is ONE vector load: 8 bytes {key, id} for 32-bit keys,
+// 16 bytes {key, id} for 64-bit keys; empty = all ones.
+template <typename Key> struct HashSlot;
+template <> struct HashSlot<uint32_t> {
+    static constexpr int kWords = 1;                       // 64-bit words per slot
+    __device__ static __forceinline__ bool try_insert(unsigned long long* table, uint32_t slot, uint32_t key, uint32_t id)
+    {
+        return atomicCAS(&table[slot], ~0ull, (unsigned long long)key | ((unsigned long long)id << 32)) == ~0ull;
+    }
+    // 1 = found (id set), 0 = empty slot (key absent), -1 = other key (keep probing)
+    __device__ static __forceinline__ int probe(const unsigned long long* table, uint32_t slot, uint32_t key, uint32_t& id)
+    {
+        const unsigned long long e = __ldg(&table[slot]);
+        if ((uint32_t)e == key) { id = (uint32_t)(e >> 32); return 1; }
+        return e == ~0ull ? 0 : -1;
+    }
+};
+template <> struct HashSlot<uint64_t> {
+    static constexpr int kWords = 2;
+    __device__ static __forceinline__ bool try_insert(unsigned long long* table, uint32_t slot, uint64_t key, uint32_t id)
+    {
+        if (atomicCAS(&table[2ull * slot], ~0ull, (unsigned long long)key) != ~0ull) return false;
+        table[2ull * slot + 1] = id;
+        return true;
+    }
+    __device__ static __forceinline__ int probe(const unsigned long long* table, uint32_t slot, uint64_t key, uint32_t& id)
+    {
+        const ulonglong2 e = __ldg(reinterpret_cast<const ulonglong2*>(table) + slot);
+        if (e.x == key) { id = (uint32_t)e.y; return 1; }
+        return e.x == ~0ull ? 0 : -1;
+    }
+};
+
 // ---- order preserving float <-> uint mapping for atomic min / max
 __device__ __forceinline__ uint32_t float_to_ordered(float f)
 {

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kCellThreads) count_heads_kernel(const Key* __
 template <typename Key>
 __global__ void __launch_bounds__(kCellThreads) emit_cells_kernel(const Key* __restrict__ keys, int n, const uint32_t* __restrict__ tile_base,
                                                                   Key* __restrict__ cell_key, uint32_t* __restrict__ cell_start,
-                                                                  Key* __restrict__ hkeys, uint32_t* __restrict__ hvals, int hash_log2)
+                                                                  unsigned long long* __restrict__ htable, int hash_log2)
 {
     __shared__ uint32_t warp_sums[8];
     const int base = blockIdx.x * kCellTile + threadIdx.x * kCellItems;
@@ -170,8 +170,7 @@ __global__ void __launch_bounds__(kCellThreads) emit_cells_kernel(const Key* __r
             cell_start[cid] = (uint32_t)(base + i);
             uint32_t slot = Morton<Key>::hash(k[i]) >> (32 - hash_log2);
             for (;;) {
-                const Key old = cas_key(&hkeys[slot], Morton<Key>::kEmpty, k[i]);
-                if (old == Morton<Key>::kEmpty) { hvals[slot] = cid; break; }
+                if (HashSlot<Key>::try_insert(htable, slot, k[i], cid)) break;
                 slot = (slot + 1) & hmask;
             }
             cid++;

@@ -28,7 +28,7 @@ constexpr int kQueryBlocksPerSM = 3;
 constexpr int kStageInts = 1536;          // per-warp staging capacity (ints)
 constexpr int kStageRecs = 192;           // per-warp staged list records
 constexpr int kCellsPerTicket = 8;
-// per-warp shared memory (ints): stage | rec_idx | rec_off | run_start[32] | run_pre[32] | query float4[32] | query r2[32]
+// per-warp shared memory (ints): stage | rec_idx | rec_off | run_base[32] | (32 spare) | query float4[32] | query r2[32]
 constexpr int kOffRecIdx = kStageInts;
 constexpr int kOffRecOff = kOffRecIdx + kStageRecs;
 constexpr int kOffRunStart = kOffRecOff + kStageRecs;
@@ -52,21 +52,18 @@ struct QueryArgs {
     const float4* c_pts;
     const float* c_r2;
     const uint32_t* c_cell_start;
-    const Key* hkeys;
-    const uint32_t* hvals;
+    const unsigned long long* htable;   // HashSlot<Key> slots: cell key -> compact cell id
     int hash_log2;
     int same_set;
-    int max_coord;
+    Key key_mask;                 // (1 << 3*bits) - 1
     float r2_fixed;
     // output
     int32_t* ragged;
     long long capacity;
     long long* list_pos;
-    unsigned long long* cursor;   // next free int of the ragged buffer
+    unsigned long long* cursor;   // next free int of the ragged buffer (always a multiple of 4)
     uint32_t* ticket;
     unsigned long long* n_neighbors;
-    int* nb_min;
-    int* nb_max;
     int* overflow;
 };
 
@@ -74,26 +71,35 @@ struct WarpStage {
     int* ints;       // [kStageInts]  staged lists  [n, j0, j1, ...]
     int* rec_idx;    // [kStageRecs]  query index of every staged list
     int* rec_off;    // [kStageRecs]  its offset inside ints
-    int* run_start;  // [32]
-    int* run_pre;    // [32]
+    int* run_base;   // [32]          (start - prefix) of the non-empty neighbour runs, compacted
     int wpos;
     int nrec;
+    unsigned nb_sum;              // neighbour ids written by this warp (flushed to the 64-bit global counter before it can wrap)
 };
 
+// write-once data: streaming stores keep the lists from evicting the candidate tiles out of L2
+__device__ __forceinline__ void st_stream_i4(int4* p, const int4& v) { __stcs(p, v); }
+
+// Flush the staged lists: ONE atomicAdd reserves a 16-byte aligned range of the ragged buffer, the copy runs as 128-bit
+// loads / stores, then list_pos is published for the staged queries.
 template <typename Key>
 __device__ __forceinline__ void stage_flush(WarpStage& st, const QueryArgs<Key>& a, int lane)
 {
     __syncwarp();
     if (st.wpos > 0) {
+        const int w4 = (st.wpos + 3) & ~3;
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(a.cursor, (unsigned long long)st.wpos);
+        if (lane == 0) base = atomicAdd(a.cursor, (unsigned long long)w4);
         base = __shfl_sync(kFull, base, 0);
-        if ((long long)(base + st.wpos) <= a.capacity) {
-            for (int t = lane; t < st.wpos; t += 32) a.ragged[base + t] = st.ints[t];
+        if ((long long)(base + w4) <= a.capacity) {
+            const int4* src = reinterpret_cast<const int4*>(st.ints);
+            int4* dst = reinterpret_cast<int4*>(a.ragged + base);
+            for (int t = lane; t < (w4 >> 2); t += 32) st_stream_i4(dst + t, src[t]);
             for (int k = lane; k < st.nrec; k += 32) a.list_pos[st.rec_idx[k]] = (long long)base + st.rec_off[k];
         } else if (lane == 0) {
             *a.overflow = 1;
         }
+        st.nb_sum += (unsigned)(st.wpos - st.nrec);
     }
     st.wpos = 0;
     st.nrec = 0;
@@ -107,10 +113,11 @@ __device__ __forceinline__ int* reserve_list(WarpStage& st, const QueryArgs<Key>
 {
     ok = true;
     if (n + 1 > kStageInts) {
+        const unsigned long long need = (unsigned long long)((n + 1 + 3) & ~3);
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(a.cursor, (unsigned long long)(n + 1));
+        if (lane == 0) base = atomicAdd(a.cursor, need);
         base = __shfl_sync(kFull, base, 0);
-        if ((long long)(base + n + 1) > a.capacity) {
+        if ((long long)(base + need) > a.capacity) {
             if (lane == 0) *a.overflow = 1;
             ok = false;
             return nullptr;
@@ -119,6 +126,8 @@ __device__ __forceinline__ int* reserve_list(WarpStage& st, const QueryArgs<Key>
             a.ragged[base] = n;
             a.list_pos[qidx] = (long long)base;
         }
+        st.nb_sum += (unsigned)n;
+        if (st.nb_sum > 0x40000000u) { if (lane == 0) atomicAdd(a.n_neighbors, (unsigned long long)st.nb_sum); st.nb_sum = 0; }
         return a.ragged + base;
     }
     if (st.wpos + n + 1 > kStageInts || st.nrec == kStageRecs) stage_flush(st, a, lane);
@@ -193,15 +202,22 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
     return r;
 }
 
-// candidate t of the dense list -> position in the sorted array of set_j (5-step search of the 32-entry run table)
-__device__ __forceinline__ int candidate_pos(const WarpStage& st, int t)
-{
-    int rho = 0;
-#pragma unroll
-    for (int step = 16; step >= 1; step >>= 1)
-        if (st.run_pre[rho + step] <= t) rho += step;
-    return st.run_start[rho] + (t - st.run_pre[rho]);
-}
+// The dense candidate list of a cell is the concatenation of its (up to 27) non-empty neighbour runs.  RunTable answers
+// "which position of the sorted array is candidate t" for the 32 consecutive candidates of one slot with one REDUX.OR,
+// one VOTE and a popc per lane (no per-lane search): bit b of `starts` says that a run begins at candidate base+b.
+struct RunTable {
+    int pre;         // this lane's run: first candidate number (exclusive prefix of the run lengths)
+    int cnt;         // this lane's run: length (0 = no run on this lane)
+    const int* run_base;
+    __device__ __forceinline__ int pos(int slot_base, int lane) const
+    {
+        const bool starts_here = cnt > 0 && pre >= slot_base && pre < slot_base + 32;
+        const unsigned starts = __reduce_or_sync(kFull, starts_here ? (1u << (pre - slot_base)) : 0u);
+        const int before = __popc(__ballot_sync(kFull, cnt > 0 && pre < slot_base));
+        const int k = before + __popc(starts & (0xffffffffu >> (31 - lane))) - 1;
+        return run_base[max(k, 0)] + slot_base + lane;
+    }
+};
 
 template <typename Key, int NSLOT, bool VARIABLE, bool SYMMETRIC>
 __global__ void __launch_bounds__(kQueryThreads, NSLOT <= 8 ? kQueryBlocksPerSM : 2) query_kernel(const QueryArgs<Key> a)
@@ -213,23 +229,18 @@ __global__ void __launch_bounds__(kQueryThreads, NSLOT <= 8 ? kQueryBlocksPerSM 
     st.ints = s_mem + warp * kWarpSmemInts;
     st.rec_idx = st.ints + kOffRecIdx;
     st.rec_off = st.ints + kOffRecOff;
-    st.run_start = st.ints + kOffRunStart;
-    st.run_pre = st.ints + kOffRunPre;
+    st.run_base = st.ints + kOffRunStart;
     float4* qbuf = reinterpret_cast<float4*>(st.ints + kOffQbuf);
     float* qr2s = reinterpret_cast<float*>(st.ints + kOffQr2);
     st.wpos = 0;
     st.nrec = 0;
+    st.nb_sum = 0;
 
-    // neighbour cell offset owned by this lane (lanes 27..31 idle during the lookup)
-    const int ox = lane % 3 - 1, oy = (lane / 3) % 3 - 1, oz = lane / 9 - 1;
     const uint32_t hmask = (1u << a.hash_log2) - 1u;
     const unsigned lt = lanemask_lt();
     const float r2_fixed = a.r2_fixed;
     const int query_limit = a.query_limit;
     const bool same_set = a.same_set != 0;
-
-    unsigned long long nb_sum = 0;
-    int nb_lo = 0x7fffffff, nb_hi = 0;
 
     for (;;) {
         uint32_t c0 = 0;
@@ -242,34 +253,43 @@ __global__ void __launch_bounds__(kQueryThreads, NSLOT <= 8 ? kQueryBlocksPerSM 
             // ---------------- the 27 neighbour runs of this cell
             const Key key = a.q_cell_key[c];
             const int qb = (int)a.q_cell_start[c], qe = (int)a.q_cell_start[c + 1];
-            int cx, cy, cz;
-            Morton<Key>::decode(key, cx, cy, cz);
             int rs = 0, rc = 0;
             {
-                const int nx = cx + ox, ny = cy + oy, nz = cz + oz;
-                if (lane < 27 && nx >= 0 && ny >= 0 && nz >= 0 && nx <= a.max_coord && ny <= a.max_coord && nz <= a.max_coord) {
-                    const Key nkey = Morton<Key>::encode((uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
+                // neighbour cell offset owned by this lane (lanes 27..31 idle during the lookup).  The opaque copy of the lane id
+                // keeps the per-lane Morton constants from being hoisted out of the cell loop, where they would cost ~10
+                // registers for the whole kernel.
+                int l = lane;
+                asm volatile("" : "+r"(l));
+                const int ox = l % 3 - 1, oy = (l / 3) % 3 - 1, oz = l / 9 - 1;
+                bool valid = l < 27;
+                const Key nkey = morton_neighbor<Key>(key, ox, oy, oz, a.key_mask, valid);
+                if (valid) {
                     uint32_t slot = Morton<Key>::hash(nkey) >> (32 - a.hash_log2);
                     for (;;) {
-                        const Key k = a.hkeys[slot];
-                        if (k == nkey) {
-                            const uint32_t cid = a.hvals[slot];
+                        uint32_t cid;
+                        const int r = HashSlot<Key>::probe(a.htable, slot, nkey, cid);
+                        if (r > 0) {
                             rs = (int)a.c_cell_start[cid];
                             rc = (int)a.c_cell_start[cid + 1] - rs;
-                            break;
                         }
-                        if (k == Morton<Key>::kEmpty) break;
+                        if (r >= 0) break;
                         slot = (slot + 1) & hmask;
                     }
                 }
             }
             const int inc = warp_inclusive_scan(rc, lane);
             const int T = __shfl_sync(kFull, inc, 31);
-            __syncwarp();
-            st.run_start[lane] = rs;
-            st.run_pre[lane] = inc - rc;
-            __syncwarp();
-            const int self_pre = a.same_set ? st.run_pre[13] : 0;   // lane 13 = offset (0,0,0)
+            RunTable runs;
+            runs.pre = inc - rc;
+            runs.cnt = rc;
+            runs.run_base = st.run_base;
+            {
+                const unsigned nonempty = __ballot_sync(kFull, rc > 0);
+                __syncwarp();
+                if (rc > 0) st.run_base[__popc(nonempty & lt)] = rs - runs.pre;
+                __syncwarp();
+            }
+            const int self_pre = __shfl_sync(kFull, runs.pre, 13);   // lane 13 = offset (0,0,0): the cell itself when same_set
 
             if (T <= NSLOT * 32) {
                 // ---------------- fast path: the whole candidate list lives in registers, two slots per packed register
@@ -278,107 +298,121 @@ __global__ void __launch_bounds__(kQueryThreads, NSLOT <= 8 ? kQueryBlocksPerSM 
                 float pr2[SYMMETRIC ? NSLOT : 1];
 #pragma unroll
                 for (int j = 0; j < NSLOT / 2; j++) {
-                    float x[2] = { 3.0e38f, 3.0e38f }, y[2] = { 0.0f, 0.0f }, z[2] = { 0.0f, 0.0f };
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const int s = 2 * j + h;
-                        pid[s] = -1;
-                        if (SYMMETRIC) pr2[s] = -1.0f;
-                        if (s * 32 < T) {
-                            const int t = s * 32 + lane;
-                            if (t < T) {
-                                const int pos = candidate_pos(st, t);
-                                const float4 v = a.c_pts[pos];
-                                x[h] = v.x; y[h] = v.y; z[h] = v.z; pid[s] = __float_as_int(v.w);
-                                if (SYMMETRIC) pr2[s] = a.c_r2[pos];
-                            }
+                    // a lane without a candidate holds a point at x = 3e38: d2 = inf, never a hit (and r2 = -1 for the symmetric test)
+                    float4 v0 = make_float4(3.0e38f, 0.0f, 0.0f, __int_as_float(-1)), v1 = v0;
+                    float w0 = -1.0f, w1 = -1.0f;
+                    if (2 * j * 32 < T) {
+                        const int pos = runs.pos(2 * j * 32, lane);
+                        if (2 * j * 32 + lane < T) {
+                            v0 = a.c_pts[pos];
+                            if (SYMMETRIC) w0 = a.c_r2[pos];
                         }
                     }
-                    px[j] = settle2(pack2(x[0], x[1])); py[j] = settle2(pack2(y[0], y[1])); pz[j] = settle2(pack2(z[0], z[1]));
+                    if ((2 * j + 1) * 32 < T) {
+                        const int pos = runs.pos((2 * j + 1) * 32, lane);
+                        if ((2 * j + 1) * 32 + lane < T) {
+                            v1 = a.c_pts[pos];
+                            if (SYMMETRIC) w1 = a.c_r2[pos];
+                        }
+                    }
+                    px[j] = settle2(pack2(v0.x, v1.x));
+                    py[j] = settle2(pack2(v0.y, v1.y));
+                    pz[j] = settle2(pack2(v0.z, v1.z));
+                    pid[2 * j] = __float_as_int(v0.w);
+                    pid[2 * j + 1] = __float_as_int(v1.w);
+                    if (SYMMETRIC) { pr2[2 * j] = w0; pr2[2 * j + 1] = w1; }
                 }
-                // number of packed slot pairs in use; the query loop is instantiated per count so that its body is straight-line
-                const int npairs = (T + 63) >> 6;
-                auto run_queries = [&](auto np_tag) {
+                // number of packed slot pairs in use; the query loop is instantiated per count so that its body is straight-line.
+                // It returns early when the staging buffer cannot take another worst-case list; the flush lives in ONE place
+                // outside the specialised loops (inlining it into each of them costs registers in the hot loop).
+                // (the 16-slot variant only instantiates 2, 4, 6 and 8 pairs; unused pairs hold far-away points)
+                const int npairs_exact = max((T + 63) >> 6, 1);
+                const int npairs = NSLOT == 8 ? npairs_exact : min((npairs_exact + 1) & ~1, NSLOT / 2);
+                auto run_queries = [&](auto np_tag, int k, const int nq, const int q0) -> int {
                     constexpr int NP = decltype(np_tag)::value;
-                    for (int q0 = qb; q0 < qe; q0 += 32) {
-                        const int qi = q0 + lane;
-                        __syncwarp();
-                        if (qi < qe) {
-                            qbuf[lane] = a.q_pts[qi];
-                            if (VARIABLE) qr2s[lane] = a.q_r2[qi];
-                        }
-                        __syncwarp();
-                        const int nq = min(32, qe - q0);
-                        for (int k = 0; k < nq; k++) {
-                            const float4 q = qbuf[k];
-                            const int qidx = __float_as_int(q.w);
-                            if (qidx >= query_limit) continue;
-                            const float r2 = VARIABLE ? qr2s[k] : r2_fixed;
-                            if (st.wpos + 1 + NP * 64 > kStageInts || st.nrec == kStageRecs) stage_flush(st, a, lane);
-                            int* dst = st.ints + st.wpos + 1;
-                            // candidate t = s*32 + lane is the query itself  <=>  s*32 == selfkey  (never true when selfkey < 0)
-                            const int selfkey = same_set ? self_pre + (q0 + k - qb) - lane : -1;
-                            const f32x2 qx = pack2(q.x, q.x), qy = pack2(q.y, q.y), qz = pack2(q.z, q.z);
-                            int n = 0;
+                    for (; k < nq; k++) {
+                        if (st.wpos + 1 + NP * 64 > kStageInts || st.nrec == kStageRecs) return k;
+                        const float4 q = qbuf[k];
+                        const int qidx = __float_as_int(q.w);
+                        if (qidx >= query_limit) continue;
+                        const float r2 = VARIABLE ? qr2s[k] : r2_fixed;
+                        int* dst = st.ints + st.wpos + 1;
+                        // candidate t = s*32 + lane is the query itself  <=>  s*32 == selfkey  (never true when selfkey < 0)
+                        const int selfkey = same_set ? self_pre + (q0 + k - qb) - lane : -1;
+                        const f32x2 qx = pack2(q.x, q.x), qy = pack2(q.y, q.y), qz = pack2(q.z, q.z);
+                        int n = 0;
 #pragma unroll
-                            for (int j = 0; j < NP; j++) {
-                                const f32x2 dx = sub2(qx, px[j]);
-                                const f32x2 dy = sub2(qy, py[j]);
-                                const f32x2 dz = sub2(qz, pz[j]);
-                                const f32x2 d2p = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
-                                float d2[2];
-                                unpack2(d2p, d2[0], d2[1]);
+                        for (int j = 0; j < NP; j++) {
+                            const f32x2 dx = sub2(qx, px[j]);
+                            const f32x2 dy = sub2(qy, py[j]);
+                            const f32x2 dz = sub2(qz, pz[j]);
+                            const f32x2 d2p = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+                            float d2[2];
+                            unpack2(d2p, d2[0], d2[1]);
 #pragma unroll
-                                for (int h = 0; h < 2; h++) {
-                                    const int s = 2 * j + h;
-                                    bool hit = d2[h] <= r2;
-                                    if (SYMMETRIC) hit = hit || (d2[h] <= pr2[s]);
-                                    hit = hit && (selfkey != s * 32);
-                                    const unsigned m = __ballot_sync(kFull, hit);
-                                    if (hit) dst[n + __popc(m & lt)] = pid[s];
-                                    n += __popc(m);
-                                }
+                            for (int h = 0; h < 2; h++) {
+                                const int s = 2 * j + h;
+                                bool hit = d2[h] <= r2;
+                                if (SYMMETRIC) hit = hit || (d2[h] <= pr2[s]);
+                                hit = hit && (selfkey != s * 32);
+                                const unsigned m = __ballot_sync(kFull, hit);
+                                if (hit) dst[n + __popc(m & lt)] = pid[s];
+                                n += __popc(m);
                             }
-                            if (lane == 0) {
-                                dst[-1] = n;
-                                st.rec_idx[st.nrec] = qidx;
-                                st.rec_off[st.nrec] = st.wpos;
-                            }
-                            st.wpos += n + 1;
-                            st.nrec += 1;
-                            nb_sum += (unsigned long long)n;
-                            nb_lo = min(nb_lo, n);
-                            nb_hi = max(nb_hi, n);
                         }
+                        if (lane == 0) {
+                            dst[-1] = n;
+                            st.rec_idx[st.nrec] = qidx;
+                            st.rec_off[st.nrec] = st.wpos;
+                        }
+                        st.wpos += n + 1;
+                        st.nrec += 1;
                     }
+                    return nq;
                 };
-                if (NSLOT == 8) {
-                    switch (npairs) {
-                    case 0: case 1: run_queries(std::integral_constant<int, 1>{}); break;
-                    case 2: run_queries(std::integral_constant<int, 2>{}); break;
-                    case 3: run_queries(std::integral_constant<int, 3>{}); break;
-                    default: run_queries(std::integral_constant<int, 4>{}); break;
+                for (int q0 = qb; q0 < qe; q0 += 32) {
+                    const int qi = q0 + lane;
+                    __syncwarp();
+                    if (qi < qe) {
+                        qbuf[lane] = a.q_pts[qi];
+                        if (VARIABLE) qr2s[lane] = a.q_r2[qi];
                     }
-                } else {
-                    if (npairs <= 2) run_queries(std::integral_constant<int, (NSLOT >= 4 ? 2 : NSLOT / 2)>{});
-                    else if (npairs <= 4) run_queries(std::integral_constant<int, (NSLOT >= 8 ? 4 : NSLOT / 2)>{});
-                    else if (npairs <= 6) run_queries(std::integral_constant<int, (NSLOT >= 12 ? 6 : NSLOT / 2)>{});
-                    else run_queries(std::integral_constant<int, NSLOT / 2>{});
+                    __syncwarp();
+                    const int nq = min(32, qe - q0);
+                    int k = 0;
+                    while (k < nq) {
+                        if (st.wpos + 1 + npairs * 64 > kStageInts || st.nrec == kStageRecs) stage_flush(st, a, lane);
+                        if (NSLOT == 8) {
+                            switch (npairs) {
+                            case 1: k = run_queries(std::integral_constant<int, 1>{}, k, nq, q0); break;
+                            case 2: k = run_queries(std::integral_constant<int, 2>{}, k, nq, q0); break;
+                            case 3: k = run_queries(std::integral_constant<int, 3>{}, k, nq, q0); break;
+                            default: k = run_queries(std::integral_constant<int, 4>{}, k, nq, q0); break;
+                            }
+                        } else {
+                            // npairs is already rounded to the instantiated counts, so the room check above and the one
+                            // inside run_queries agree (otherwise this loop could spin without making progress)
+                            if (npairs == 2) k = run_queries(std::integral_constant<int, 2>{}, k, nq, q0);
+                            else if (npairs == 4) k = run_queries(std::integral_constant<int, 4>{}, k, nq, q0);
+                            else if (npairs == 6) k = run_queries(std::integral_constant<int, 6>{}, k, nq, q0);
+                            else k = run_queries(std::integral_constant<int, NSLOT / 2>{}, k, nq, q0);
+                        }
+                    }
                 }
             } else {
                 // ---------------- general path (very dense neighbourhoods): two sweeps per query, candidates re-read through L1
                 for (int qi = qb; qi < qe; qi++) {
                     const float4 qv = a.q_pts[qi];
                     const int qidx = __float_as_int(qv.w);
-                    if (qidx >= a.query_limit) continue;
-                    const float r2 = VARIABLE ? a.q_r2[qi] : a.r2_fixed;
-                    const int ts = a.same_set ? self_pre + (qi - qb) : -1;
+                    if (qidx >= query_limit) continue;
+                    const float r2 = VARIABLE ? a.q_r2[qi] : r2_fixed;
+                    const int ts = same_set ? self_pre + (qi - qb) : -1;
                     int n = 0;
                     for (int t0 = 0; t0 < T; t0 += 32) {
                         const int t = t0 + lane;
+                        const int pos = runs.pos(t0, lane);
                         bool h = false;
                         if (t < T && t != ts) {
-                            const int pos = candidate_pos(st, t);
                             const float4 v = a.c_pts[pos];
                             const float d2 = dist2(qv.x, qv.y, qv.z, v.x, v.y, v.z);
                             h = d2 <= r2;
@@ -386,19 +420,16 @@ __global__ void __launch_bounds__(kQueryThreads, NSLOT <= 8 ? kQueryBlocksPerSM 
                         }
                         n += __popc(__ballot_sync(kFull, h));
                     }
-                    nb_sum += (unsigned long long)n;
-                    nb_lo = min(nb_lo, n);
-                    nb_hi = max(nb_hi, n);
                     bool ok;
                     int* dst = reserve_list(st, a, lane, qidx, n, ok);
                     if (!ok) continue;
                     int p = 1;
                     for (int t0 = 0; t0 < T; t0 += 32) {
                         const int t = t0 + lane;
+                        const int pos = runs.pos(t0, lane);
                         bool h = false;
                         int id = -1;
                         if (t < T && t != ts) {
-                            const int pos = candidate_pos(st, t);
                             const float4 v = a.c_pts[pos];
                             const float d2 = dist2(qv.x, qv.y, qv.z, v.x, v.y, v.z);
                             h = d2 <= r2;
@@ -414,10 +445,23 @@ __global__ void __launch_bounds__(kQueryThreads, NSLOT <= 8 ? kQueryBlocksPerSM 
         }
     }
     stage_flush(st, a, lane);
-    if (lane == 0) {
-        if (nb_sum) atomicAdd(a.n_neighbors, nb_sum);
-        if (nb_lo != 0x7fffffff) atomicMin(a.nb_min, nb_lo);
-        atomicMax(a.nb_max, nb_hi);
+    if (lane == 0 && st.nb_sum) atomicAdd(a.n_neighbors, (unsigned long long)st.nb_sum);
+}
+
+// [min, max] of the list lengths of one pair (print_state's "n_neighbors [min, max, avg]"), computed on demand
+__global__ void __launch_bounds__(256) list_minmax_kernel(const int32_t* __restrict__ ragged, const long long* __restrict__ list_pos, int n_lists, int* __restrict__ out)
+{
+    int lo = 0x7fffffff, hi = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_lists; i += gridDim.x * blockDim.x) {
+        const int n = ragged[list_pos[i]];
+        lo = min(lo, n);
+        hi = max(hi, n);
+    }
+    lo = __reduce_min_sync(kFull, lo);
+    hi = __reduce_max_sync(kFull, hi);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&out[0], lo);
+        atomicMax(&out[1], hi);
     }
 }
 

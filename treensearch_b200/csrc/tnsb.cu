@@ -66,9 +66,8 @@ struct PairCounters {
     unsigned long long cursor;
     unsigned long long n_neighbors;
     uint32_t ticket;
-    int nb_min;
-    int nb_max;
     int overflow;
+    int minmax[2];
 };
 
 struct SetState {
@@ -90,7 +89,7 @@ struct SetState {
     int sel = 0;
     DevBuf sorted, sorted_r2;
     DevBuf cell_key, cell_start, tile_heads;
-    DevBuf hkeys, hvals;
+    DevBuf htable;
     int hash_log2 = 1;
     int n_cells = 0;
     bool sorted_valid = false;     // "are_cells_valid" of the reference (TreeNSearch.cpp:148)
@@ -284,16 +283,16 @@ int build_sets(tnsb_context* c, const GridParams& gp)
         while ((1ll << lg) < 2ll * st.n_cells) lg++;
         st.hash_log2 = lg;
         const size_t hs = (size_t)1 << lg;
-        TNSB_CUDA(c, st.hkeys.ensure(sizeof(Key) * hs, 1.25));
-        TNSB_CUDA(c, st.hvals.ensure(sizeof(uint32_t) * hs, 1.25));
-        TNSB_CUDA(c, cudaMemsetAsync(st.hkeys.p, 0xff, sizeof(Key) * hs, s));
+        const size_t hbytes = sizeof(unsigned long long) * HashSlot<Key>::kWords * hs;
+        TNSB_CUDA(c, st.htable.ensure(hbytes, 1.25));
+        TNSB_CUDA(c, cudaMemsetAsync(st.htable.p, 0xff, hbytes, s));
         c->stats.n_cells += st.n_cells;
         if (st.n == 0) continue;
         TNSB_CUDA(c, st.cell_key.ensure(sizeof(Key) * ((size_t)st.n_cells + 1), 1.25));
         TNSB_CUDA(c, st.cell_start.ensure(sizeof(uint32_t) * ((size_t)st.n_cells + 2), 1.25));
         const int n_tiles = ceil_div(st.n, kCellTile);
         emit_cells_kernel<Key><<<n_tiles, kCellThreads, 0, s>>>(st.keys[st.sel].as<Key>(), st.n, st.tile_heads.as<uint32_t>(), st.cell_key.as<Key>(),
-                                                              st.cell_start.as<uint32_t>(), st.hkeys.as<Key>(), st.hvals.as<uint32_t>(), st.hash_log2);
+                                                              st.cell_start.as<uint32_t>(), st.htable.as<unsigned long long>(), st.hash_log2);
         launches++;
         st.sorted_valid = true;
     }
@@ -332,11 +331,10 @@ int query_pair(tnsb_context* c, int si, int sj, const GridParams& gp, PairCounte
     a.c_pts = cj.sorted.as<float4>();
     a.c_r2 = cj.sorted_r2.as<float>();
     a.c_cell_start = cj.cell_start.as<uint32_t>();
-    a.hkeys = cj.hkeys.as<Key>();
-    a.hvals = cj.hvals.as<uint32_t>();
+    a.htable = cj.htable.as<unsigned long long>();
     a.hash_log2 = cj.hash_log2;
     a.same_set = si == sj;
-    a.max_coord = gp.max_coord;
+    a.key_mask = (Key)(((Key)1 << (3 * gp.bits)) - 1);
     a.r2_fixed = c->radius_sq;
     a.ragged = ps.d_ragged.as<int32_t>();
     a.capacity = ps.capacity;
@@ -344,8 +342,6 @@ int query_pair(tnsb_context* c, int si, int sj, const GridParams& gp, PairCounte
     a.cursor = &d_cnt->cursor;
     a.ticket = &d_cnt->ticket;
     a.n_neighbors = &d_cnt->n_neighbors;
-    a.nb_min = &d_cnt->nb_min;
-    a.nb_max = &d_cnt->nb_max;
     a.overflow = &d_cnt->overflow;
     const bool variable = !c->radius_set;
     const bool symmetric = variable && c->symmetric;   // TreeNSearch.cpp:2431
@@ -533,7 +529,6 @@ int run_impl(tnsb_context* c)
         for (int id : todo) {
             PairCounters z;
             memset(&z, 0, sizeof(z));
-            z.nb_min = INT_MAX;
             h_init[id] = z;
         }
         for (int id : todo)
@@ -560,8 +555,7 @@ int run_impl(tnsb_context* c)
             } else {
                 ps.n_ints = (int64_t)r.cursor;
                 ps.n_neighbors = (int64_t)r.n_neighbors;
-                ps.nb_min = r.nb_min == INT_MAX ? 0 : r.nb_min;
-                ps.nb_max = r.nb_max;
+                ps.nb_min = ps.nb_max = -1;       // computed on demand (tnsb_get_pair_neighbor_stats)
             }
         }
         todo.swap(again);
@@ -681,7 +675,7 @@ void tnsb_destroy(tnsb_context* c)
         st.up_pts.release(); st.up_radii.release(); st.cv_pts.release(); st.cv_radii.release();
         for (int b = 0; b < 2; b++) { st.keys[b].release(); st.vals[b].release(); }
         st.sorted.release(); st.sorted_r2.release(); st.cell_key.release(); st.cell_start.release(); st.tile_heads.release();
-        st.hkeys.release(); st.hvals.release(); st.d_zorder.release();
+        st.htable.release(); st.d_zorder.release();
     }
     for (auto& p : c->pairs) { p.d_ragged.release(); p.d_list_pos.release(); p.h_ragged.release(); p.h_list_pos.release(); }
     c->d_reduce.release(); c->d_counters.release(); c->d_misc.release(); c->sort_temp.release(); c->scan_temp.release(); c->h_small.release();
@@ -1039,7 +1033,23 @@ int tnsb_get_pair_neighbor_stats(const tnsb_context* c, int si, int sj, int64_t 
     if (!c || !out || si < 0 || sj < 0 || si >= (int)c->sets.size() || sj >= (int)c->sets.size()) return TNSB_ERR_INVALID_ARGUMENT;
     const size_t id = (size_t)si * c->sets.size() + sj;
     if (id >= c->pairs.size() || !c->pairs[id].valid) return TNSB_ERR_INVALID_STATE;
-    out[0] = c->pairs[id].nb_min; out[1] = c->pairs[id].nb_max; out[2] = c->pairs[id].n_neighbors;
+    PairState& ps = const_cast<tnsb_context*>(c)->pairs[id];
+    if (ps.nb_min < 0) {
+        ps.nb_min = ps.nb_max = 0;
+        if (ps.n_lists > 0) {
+            tnsb_context* m = const_cast<tnsb_context*>(c);
+            PairCounters* d = m->d_counters.as<PairCounters>() + id;
+            int* h = m->h_small.as<int>();
+            h[0] = INT_MAX; h[1] = 0;
+            cudaSetDevice(m->device);
+            cudaMemcpyAsync(d->minmax, h, 2 * sizeof(int), cudaMemcpyHostToDevice, m->stream);
+            list_minmax_kernel<<<4 * m->n_sms, 256, 0, m->stream>>>(ps.d_ragged.as<int32_t>(), ps.d_list_pos.as<long long>(), ps.n_lists, d->minmax);
+            cudaMemcpyAsync(h, d->minmax, 2 * sizeof(int), cudaMemcpyDeviceToHost, m->stream);
+            if (cudaStreamSynchronize(m->stream) != cudaSuccess) { cudaGetLastError(); return TNSB_ERR_CUDA; }
+            ps.nb_min = h[0]; ps.nb_max = h[1];
+        }
+    }
+    out[0] = ps.nb_min; out[1] = ps.nb_max; out[2] = ps.n_neighbors;
     return TNSB_OK;
 }
 
