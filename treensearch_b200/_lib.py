@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtnsb.so")
+LIB_PATH = os.environ.get("TNSB_LIB", os.path.join(_HERE, "libtnsb.so"))     # TNSB_LIB: experiment builds only
 
 TNSB_OK = 0
 TNSB_ERR_INVALID_ARGUMENT = -1

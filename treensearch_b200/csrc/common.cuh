@@ -113,37 +113,38 @@ __device__ __forceinline__ Key morton_neighbor(Key key, int ox, int oy, int oz, 
     return out;
 }
 
-// ---- open addressing hash  cell key -> compact cell id.  One slot is ONE vector load: 8 bytes {key, id} for 32-bit keys,
-// 16 bytes {key, id} for 64-bit keys; empty = all ones.
+// ---- open addressing hash  cell key -> [start, end) of the cell's run in the sorted point array.  One slot is ONE 16-byte
+// vector load {key, start, end}, so a neighbour lookup is a single memory round trip (no key -> id -> cell_start chain).
+// Empty = all ones.
 template <typename Key> struct HashSlot;
 template <> struct HashSlot<uint32_t> {
-    static constexpr int kWords = 1;                       // 64-bit words per slot
-    __device__ static __forceinline__ bool try_insert(unsigned long long* table, uint32_t slot, uint32_t key, uint32_t id)
+    typedef uint4 Raw;
+    __device__ static __forceinline__ bool try_insert(Raw* table, uint32_t slot, uint32_t key, uint32_t start, uint32_t end)
     {
-        return atomicCAS(&table[slot], ~0ull, (unsigned long long)key | ((unsigned long long)id << 32)) == ~0ull;
-    }
-    // 1 = found (id set), 0 = empty slot (key absent), -1 = other key (keep probing)
-    __device__ static __forceinline__ int probe(const unsigned long long* table, uint32_t slot, uint32_t key, uint32_t& id)
-    {
-        const unsigned long long e = __ldg(&table[slot]);
-        if ((uint32_t)e == key) { id = (uint32_t)(e >> 32); return 1; }
-        return e == ~0ull ? 0 : -1;
-    }
-};
-template <> struct HashSlot<uint64_t> {
-    static constexpr int kWords = 2;
-    __device__ static __forceinline__ bool try_insert(unsigned long long* table, uint32_t slot, uint64_t key, uint32_t id)
-    {
-        if (atomicCAS(&table[2ull * slot], ~0ull, (unsigned long long)key) != ~0ull) return false;
-        table[2ull * slot + 1] = id;
+        if (atomicCAS(&table[slot].x, 0xffffffffu, key) != 0xffffffffu) return false;
+        table[slot].y = start;
+        table[slot].z = end;
         return true;
     }
-    __device__ static __forceinline__ int probe(const unsigned long long* table, uint32_t slot, uint64_t key, uint32_t& id)
+    __device__ static __forceinline__ Raw load(const Raw* table, uint32_t slot) { return __ldg(table + slot); }
+    __device__ static __forceinline__ bool matches(const Raw& e, uint32_t key) { return e.x == key; }
+    __device__ static __forceinline__ bool is_empty(const Raw& e) { return e.x == 0xffffffffu; }
+    __device__ static __forceinline__ int start(const Raw& e) { return (int)e.y; }
+    __device__ static __forceinline__ int count(const Raw& e) { return (int)(e.z - e.y); }
+};
+template <> struct HashSlot<uint64_t> {
+    typedef ulonglong2 Raw;
+    __device__ static __forceinline__ bool try_insert(Raw* table, uint32_t slot, uint64_t key, uint32_t start, uint32_t end)
     {
-        const ulonglong2 e = __ldg(reinterpret_cast<const ulonglong2*>(table) + slot);
-        if (e.x == key) { id = (uint32_t)e.y; return 1; }
-        return e.x == ~0ull ? 0 : -1;
+        if (atomicCAS(&table[slot].x, ~0ull, (unsigned long long)key) != ~0ull) return false;
+        table[slot].y = (unsigned long long)start | ((unsigned long long)end << 32);
+        return true;
     }
+    __device__ static __forceinline__ Raw load(const Raw* table, uint32_t slot) { return __ldg(table + slot); }
+    __device__ static __forceinline__ bool matches(const Raw& e, uint64_t key) { return e.x == key; }
+    __device__ static __forceinline__ bool is_empty(const Raw& e) { return e.x == ~0ull; }
+    __device__ static __forceinline__ int start(const Raw& e) { return (int)(uint32_t)e.y; }
+    __device__ static __forceinline__ int count(const Raw& e) { return (int)((uint32_t)(e.y >> 32) - (uint32_t)e.y); }
 };
 
 // ---- order preserving float <-> uint mapping for atomic min / max

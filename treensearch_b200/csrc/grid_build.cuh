@@ -139,8 +139,7 @@ __global__ void __launch_bounds__(kCellThreads) count_heads_kernel(const Key* __
 
 template <typename Key>
 __global__ void __launch_bounds__(kCellThreads) emit_cells_kernel(const Key* __restrict__ keys, int n, const uint32_t* __restrict__ tile_base,
-                                                                  Key* __restrict__ cell_key, uint32_t* __restrict__ cell_start,
-                                                                  unsigned long long* __restrict__ htable, int hash_log2)
+                                                                  Key* __restrict__ cell_key, uint32_t* __restrict__ cell_start)
 {
     __shared__ uint32_t warp_sums[8];
     const int base = blockIdx.x * kCellTile + threadIdx.x * kCellItems;
@@ -162,22 +161,40 @@ __global__ void __launch_bounds__(kCellThreads) emit_cells_kernel(const Key* __r
     }
     uint32_t total;
     uint32_t cid = block_exclusive_scan_256(c, warp_sums, total) + tile_base[blockIdx.x];
-    const uint32_t hmask = (1u << hash_log2) - 1u;
 #pragma unroll
     for (int i = 0; i < kCellItems; i++) {
         if (head[i]) {
             cell_key[cid] = k[i];
             cell_start[cid] = (uint32_t)(base + i);
-            uint32_t slot = Morton<Key>::hash(k[i]) >> (32 - hash_log2);
-            for (;;) {
-                if (HashSlot<Key>::try_insert(htable, slot, k[i], cid)) break;
-                slot = (slot + 1) & hmask;
-            }
             cid++;
         }
     }
     // sentinel: cell_start[n_cells] = n
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kCellThreads - 1) cell_start[cid] = (uint32_t)n;
+}
+
+// hash insert of every occupied cell: key -> [start, end)
+template <typename Key>
+__global__ void __launch_bounds__(256) build_hash_kernel(const Key* __restrict__ cell_key, const uint32_t* __restrict__ cell_start, int n_cells,
+                                                         typename HashSlot<Key>::Raw* __restrict__ table, int hash_log2)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    const Key k = cell_key[c];
+    const uint32_t s = cell_start[c], e = cell_start[c + 1];
+    const uint32_t hmask = (1u << hash_log2) - 1u;
+    uint32_t slot = Morton<Key>::hash(k) >> (32 - hash_log2);
+    while (!HashSlot<Key>::try_insert(table, slot, k, s, e)) slot = (slot + 1) & hmask;
+}
+
+// dense Morton-indexed cell table {start, end}: fill for the current cells / clear the entries of the previous run
+template <typename Key>
+__global__ void __launch_bounds__(256) dense_table_kernel(const Key* __restrict__ cell_key, const uint32_t* __restrict__ cell_start, int n_cells,
+                                                          uint2* __restrict__ table, int fill)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    table[cell_key[c]] = fill ? make_uint2(cell_start[c], cell_start[c + 1]) : make_uint2(0u, 0u);
 }
 
 // gather used by tnsb_apply_zsort_device_f32

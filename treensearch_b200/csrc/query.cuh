@@ -24,10 +24,13 @@ namespace tnsb {
 
 constexpr int kQueryThreads = 256;
 constexpr int kQueryWarps = kQueryThreads / 32;
-constexpr int kQueryBlocksPerSM = 3;
+#ifndef TNSB_QUERY_BLOCKS_PER_SM
+#define TNSB_QUERY_BLOCKS_PER_SM 3
+#endif
+constexpr int kQueryBlocksPerSM = TNSB_QUERY_BLOCKS_PER_SM;
 constexpr int kStageInts = 1536;          // per-warp staging capacity (ints)
 constexpr int kStageRecs = 192;           // per-warp staged list records
-constexpr int kCellsPerTicket = 8;
+constexpr int kCellsPerTicket = 16;
 // per-warp shared memory (ints): stage | rec_idx | rec_off | run_base[32] | (32 spare) | query float4[32] | query r2[32]
 constexpr int kOffRecIdx = kStageInts;
 constexpr int kOffRecOff = kOffRecIdx + kStageRecs;
@@ -51,8 +54,8 @@ struct QueryArgs {
     // searched set (set_j)
     const float4* c_pts;
     const float* c_r2;
-    const uint32_t* c_cell_start;
-    const unsigned long long* htable;   // HashSlot<Key> slots: cell key -> compact cell id
+    const typename HashSlot<Key>::Raw* htable;   // cell key -> [start, end) of the cell's run in c_pts (sparse / huge domains)
+    const uint2* dense;           // Morton-indexed direct table {start, end} (domains of <= 2^27 cells): no probing at all
     int hash_log2;
     int same_set;
     Key key_mask;                 // (1 << 3*bits) - 1
@@ -219,7 +222,7 @@ struct RunTable {
     }
 };
 
-template <typename Key, int NSLOT, bool VARIABLE, bool SYMMETRIC>
+template <typename Key, int NSLOT, bool VARIABLE, bool SYMMETRIC, bool DENSE>
 __global__ void __launch_bounds__(kQueryThreads, NSLOT <= 8 ? kQueryBlocksPerSM : 2) query_kernel(const QueryArgs<Key> a)
 {
     static_assert(NSLOT % 2 == 0, "slots are processed in packed pairs");
@@ -249,34 +252,57 @@ __global__ void __launch_bounds__(kQueryThreads, NSLOT <= 8 ? kQueryBlocksPerSM 
         if (c0 >= (uint32_t)a.n_q_cells) break;
         const uint32_t c1 = min(c0 + (uint32_t)kCellsPerTicket, (uint32_t)a.n_q_cells);
 
-        for (uint32_t c = c0; c < c1; c++) {
-            // ---------------- the 27 neighbour runs of this cell
-            const Key key = a.q_cell_key[c];
-            const int qb = (int)a.q_cell_start[c], qe = (int)a.q_cell_start[c + 1];
+        // The batch's cell keys and query ranges arrive with ONE coalesced load per array (lanes 0..16), cells then read them by shuffle.
+        const uint32_t nb = c1 - c0;
+        Key my_key = 0;
+        int my_start = 0;
+        if ((uint32_t)lane < nb) my_key = a.q_cell_key[c0 + lane];
+        if ((uint32_t)lane <= nb) my_start = (int)a.q_cell_start[c0 + lane];
+
+        // Software pipeline over the cells of the batch: the neighbour lookup of cell c+1 is issued before the queries of cell c are
+        // processed, so its memory round trip is hidden behind that work (the lookup is ONE vector load per neighbour cell).
+        Key nkey_next = 0;
+        uint32_t slot_next = 0;
+        bool valid_next = false;
+        typename HashSlot<Key>::Raw e_next;
+        uint2 d_next = make_uint2(0u, 0u);
+        auto issue_lookup = [&](uint32_t i) {
+            const Key key = __shfl_sync(kFull, my_key, (int)i);
+            // neighbour cell offset owned by this lane (lanes 27..31 idle during the lookup).  The opaque copy of the lane id
+            // keeps the per-lane Morton constants from being hoisted out of the cell loop (they would cost ~10 registers).
+            int l = lane;
+            asm volatile("" : "+r"(l));
+            const int ox = l % 3 - 1, oy = (l / 3) % 3 - 1, oz = l / 9 - 1;
+            valid_next = l < 27;
+            nkey_next = morton_neighbor<Key>(key, ox, oy, oz, a.key_mask, valid_next);
+            if (DENSE) {
+                d_next = make_uint2(0u, 0u);
+                if (valid_next) d_next = __ldg(a.dense + nkey_next);
+            } else {
+                slot_next = Morton<Key>::hash(nkey_next) >> (32 - a.hash_log2);
+                if (valid_next) e_next = HashSlot<Key>::load(a.htable, slot_next);
+            }
+        };
+        issue_lookup(0);
+
+        for (uint32_t i = 0; i < nb; i++) {
+            // ---------------- the 27 neighbour runs of this cell: resolve the lookup issued one iteration ago
+            const int qb = __shfl_sync(kFull, my_start, (int)i), qe = __shfl_sync(kFull, my_start, (int)i + 1);
             int rs = 0, rc = 0;
-            {
-                // neighbour cell offset owned by this lane (lanes 27..31 idle during the lookup).  The opaque copy of the lane id
-                // keeps the per-lane Morton constants from being hoisted out of the cell loop, where they would cost ~10
-                // registers for the whole kernel.
-                int l = lane;
-                asm volatile("" : "+r"(l));
-                const int ox = l % 3 - 1, oy = (l / 3) % 3 - 1, oz = l / 9 - 1;
-                bool valid = l < 27;
-                const Key nkey = morton_neighbor<Key>(key, ox, oy, oz, a.key_mask, valid);
-                if (valid) {
-                    uint32_t slot = Morton<Key>::hash(nkey) >> (32 - a.hash_log2);
-                    for (;;) {
-                        uint32_t cid;
-                        const int r = HashSlot<Key>::probe(a.htable, slot, nkey, cid);
-                        if (r > 0) {
-                            rs = (int)a.c_cell_start[cid];
-                            rc = (int)a.c_cell_start[cid + 1] - rs;
-                        }
-                        if (r >= 0) break;
-                        slot = (slot + 1) & hmask;
-                    }
+            if (DENSE) {
+                rs = (int)d_next.x;
+                rc = (int)(d_next.y - d_next.x);
+            } else if (valid_next) {
+                typename HashSlot<Key>::Raw e = e_next;
+                uint32_t slot = slot_next;
+                for (;;) {
+                    if (HashSlot<Key>::matches(e, nkey_next)) { rs = HashSlot<Key>::start(e); rc = HashSlot<Key>::count(e); break; }
+                    if (HashSlot<Key>::is_empty(e)) break;
+                    slot = (slot + 1) & hmask;
+                    e = HashSlot<Key>::load(a.htable, slot);
                 }
             }
+            if (i + 1 < nb) issue_lookup(i + 1);
             const int inc = warp_inclusive_scan(rc, lane);
             const int T = __shfl_sync(kFull, inc, 31);
             RunTable runs;

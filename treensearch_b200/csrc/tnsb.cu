@@ -90,6 +90,10 @@ struct SetState {
     DevBuf sorted, sorted_r2;
     DevBuf cell_key, cell_start, tile_heads;
     DevBuf htable;
+    DevBuf dense;                  // Morton-indexed {start, end} table (small domains)
+    int dense_bits = -1;           // key bits the dense table is laid out (and zeroed) for; -1 = not valid
+    int dense_cells = 0;           // cells of the previous run whose entries are still set
+    bool use_dense = false;
     int hash_log2 = 1;
     int n_cells = 0;
     bool sorted_valid = false;     // "are_cells_valid" of the reference (TreeNSearch.cpp:148)
@@ -277,23 +281,49 @@ int build_sets(tnsb_context* c, const GridParams& gp)
     TNSB_CUDA(c, cudaStreamSynchronize(s));
     for (int si = 0; si < n_sets; si++) {
         auto& st = c->sets[si];
-        // hash table sized to <= 50% load; always at least 2 slots so that lookups into an empty set terminate
         st.n_cells = st.n > 0 ? (int)h_ncells[si] : 0;
-        int lg = 1;
-        while ((1ll << lg) < 2ll * st.n_cells) lg++;
-        st.hash_log2 = lg;
-        const size_t hs = (size_t)1 << lg;
-        const size_t hbytes = sizeof(unsigned long long) * HashSlot<Key>::kWords * hs;
-        TNSB_CUDA(c, st.htable.ensure(hbytes, 1.25));
-        TNSB_CUDA(c, cudaMemsetAsync(st.htable.p, 0xff, hbytes, s));
         c->stats.n_cells += st.n_cells;
+        // neighbour lookup structure: a dense Morton-indexed table while the grid has <= 2^27 cells (8 bytes per cell, no probing,
+        // Morton neighbours share sectors), else an open addressing hash at <= 33% load (16-byte slots {key, start, end}).
+        st.use_dense = key_bits <= 27;
+        if (st.use_dense) {
+            const size_t dbytes = sizeof(uint2) << key_bits;
+            const bool fresh = st.dense.cap < dbytes || st.dense_bits != key_bits;
+            TNSB_CUDA(c, st.dense.ensure(dbytes));
+            if (fresh) {
+                TNSB_CUDA(c, cudaMemsetAsync(st.dense.p, 0, dbytes, s));
+            } else if (st.dense_cells > 0) {
+                // un-set only what the previous run wrote (its cell keys are still in cell_key)
+                dense_table_kernel<Key><<<ceil_div(st.dense_cells, 256), 256, 0, s>>>(st.cell_key.as<Key>(), st.cell_start.as<uint32_t>(), st.dense_cells,
+                                                                                 st.dense.as<uint2>(), 0);
+                launches++;
+            }
+            st.dense_bits = key_bits;
+            st.dense_cells = 0;
+        } else {
+            st.dense_bits = -1;
+            int lg = 1;
+            while ((1ll << lg) < 3ll * st.n_cells) lg++;
+            st.hash_log2 = lg;
+            const size_t hbytes = sizeof(typename HashSlot<Key>::Raw) << lg;
+            TNSB_CUDA(c, st.htable.ensure(hbytes, 1.25));
+            TNSB_CUDA(c, cudaMemsetAsync(st.htable.p, 0xff, hbytes, s));
+        }
         if (st.n == 0) continue;
         TNSB_CUDA(c, st.cell_key.ensure(sizeof(Key) * ((size_t)st.n_cells + 1), 1.25));
         TNSB_CUDA(c, st.cell_start.ensure(sizeof(uint32_t) * ((size_t)st.n_cells + 2), 1.25));
         const int n_tiles = ceil_div(st.n, kCellTile);
         emit_cells_kernel<Key><<<n_tiles, kCellThreads, 0, s>>>(st.keys[st.sel].as<Key>(), st.n, st.tile_heads.as<uint32_t>(), st.cell_key.as<Key>(),
-                                                              st.cell_start.as<uint32_t>(), st.htable.as<unsigned long long>(), st.hash_log2);
-        launches++;
+                                                              st.cell_start.as<uint32_t>());
+        if (st.use_dense) {
+            dense_table_kernel<Key><<<ceil_div(st.n_cells, 256), 256, 0, s>>>(st.cell_key.as<Key>(), st.cell_start.as<uint32_t>(), st.n_cells,
+                                                                             st.dense.as<uint2>(), 1);
+            st.dense_cells = st.n_cells;
+        } else {
+            build_hash_kernel<Key><<<ceil_div(st.n_cells, 256), 256, 0, s>>>(st.cell_key.as<Key>(), st.cell_start.as<uint32_t>(), st.n_cells,
+                                                                            st.htable.as<typename HashSlot<Key>::Raw>(), st.hash_log2);
+        }
+        launches += 2;
         st.sorted_valid = true;
     }
     TNSB_CUDA(c, cudaEventRecord(c->ev[EV_CELLS], s));
@@ -301,7 +331,7 @@ int build_sets(tnsb_context* c, const GridParams& gp)
     return TNSB_OK;
 }
 
-template <typename Key, int NSLOT>
+template <typename Key, int NSLOT, bool DENSE>
 cudaError_t launch_query(const QueryArgs<Key>& a, bool variable, bool symmetric, int grid, cudaStream_t s)
 {
     auto go = [&](auto kernel) -> cudaError_t {
@@ -310,9 +340,9 @@ cudaError_t launch_query(const QueryArgs<Key>& a, bool variable, bool symmetric,
         kernel<<<grid, kQueryThreads, kQuerySmemBytes, s>>>(a);
         return cudaGetLastError();
     };
-    if (!variable) return go(query_kernel<Key, NSLOT, false, false>);
-    if (!symmetric) return go(query_kernel<Key, NSLOT, true, false>);
-    return go(query_kernel<Key, NSLOT, true, true>);
+    if (!variable) return go(query_kernel<Key, NSLOT, false, false, DENSE>);
+    if (!symmetric) return go(query_kernel<Key, NSLOT, true, false, DENSE>);
+    return go(query_kernel<Key, NSLOT, true, true, DENSE>);
 }
 
 template <typename Key>
@@ -330,8 +360,8 @@ int query_pair(tnsb_context* c, int si, int sj, const GridParams& gp, PairCounte
     a.query_limit = c->opt_query_limit >= 0 ? (int)std::min<int64_t>(c->opt_query_limit, INT_MAX) : INT_MAX;
     a.c_pts = cj.sorted.as<float4>();
     a.c_r2 = cj.sorted_r2.as<float>();
-    a.c_cell_start = cj.cell_start.as<uint32_t>();
-    a.htable = cj.htable.as<unsigned long long>();
+    a.htable = cj.htable.as<typename HashSlot<Key>::Raw>();
+    a.dense = cj.dense.as<uint2>();
     a.hash_log2 = cj.hash_log2;
     a.same_set = si == sj;
     a.key_mask = (Key)(((Key)1 << (3 * gp.bits)) - 1);
@@ -349,8 +379,9 @@ int query_pair(tnsb_context* c, int si, int sj, const GridParams& gp, PairCounte
     const double avg_cell = cj.n_cells > 0 ? (double)cj.n / cj.n_cells : 0.0;
     const int grid = kQueryBlocksPerSM * c->n_sms;
     cudaError_t e;
-    if (27.0 * avg_cell * 1.15 <= 256.0) e = launch_query<Key, 8>(a, variable, symmetric, grid, c->stream);
-    else e = launch_query<Key, 16>(a, variable, symmetric, grid, c->stream);
+    const bool small = 27.0 * avg_cell * 1.15 <= 256.0;
+    if (cj.use_dense) e = small ? launch_query<Key, 8, true>(a, variable, symmetric, grid, c->stream) : launch_query<Key, 16, true>(a, variable, symmetric, grid, c->stream);
+    else e = small ? launch_query<Key, 8, false>(a, variable, symmetric, grid, c->stream) : launch_query<Key, 16, false>(a, variable, symmetric, grid, c->stream);
     TNSB_CUDA(c, e);
     c->stats.n_kernel_launches++;
     c->stats.n_query_launches++;
@@ -675,7 +706,7 @@ void tnsb_destroy(tnsb_context* c)
         st.up_pts.release(); st.up_radii.release(); st.cv_pts.release(); st.cv_radii.release();
         for (int b = 0; b < 2; b++) { st.keys[b].release(); st.vals[b].release(); }
         st.sorted.release(); st.sorted_r2.release(); st.cell_key.release(); st.cell_start.release(); st.tile_heads.release();
-        st.htable.release(); st.d_zorder.release();
+        st.htable.release(); st.dense.release(); st.d_zorder.release();
     }
     for (auto& p : c->pairs) { p.d_ragged.release(); p.d_list_pos.release(); p.h_ragged.release(); p.h_list_pos.release(); }
     c->d_reduce.release(); c->d_counters.release(); c->d_misc.release(); c->sort_temp.release(); c->scan_temp.release(); c->h_small.release();
