@@ -24,23 +24,27 @@ namespace tnsb {
 
 constexpr int kQueryThreads = 256;
 constexpr int kQueryWarps = kQueryThreads / 32;
-#ifndef TNSB_QUERY_BLOCKS_PER_SM
-#define TNSB_QUERY_BLOCKS_PER_SM 3
-#endif
-constexpr int kQueryBlocksPerSM = TNSB_QUERY_BLOCKS_PER_SM;
-constexpr int kStageInts = 1536;          // per-warp staging capacity (ints)
-constexpr int kStageRecs = 192;           // per-warp staged list records
 constexpr int kCellsPerTicket = 16;
-// per-warp shared memory (ints): stage | rec_idx | rec_off | run_base[32] | (32 spare) | query float4[32] | query r2[32]
-constexpr int kOffRecIdx = kStageInts;
-constexpr int kOffRecOff = kOffRecIdx + kStageRecs;
-constexpr int kOffRunStart = kOffRecOff + kStageRecs;
-constexpr int kOffRunPre = kOffRunStart + 32;
-constexpr int kOffQbuf = kOffRunPre + 32;        // must be a multiple of 4 ints (float4 alignment)
-constexpr int kOffQr2 = kOffQbuf + 128;
-constexpr int kWarpSmemInts = kOffQr2 + 32;
-constexpr int kQuerySmemBytes = kQueryWarps * kWarpSmemInts * 4;
-static_assert(kOffQbuf % 4 == 0 && kWarpSmemInts % 4 == 0, "float4 alignment of the per-warp query buffer");
+
+// per-warp shared memory layout (in ints)
+template <int NSLOT, bool SYMMETRIC>
+struct QLayout {
+    static constexpr int kStageInts = NSLOT <= 8 ? 1280 : 2048;   // staged lists [n, j0, j1, ...]; must hold one worst-case list
+    static constexpr int kStageRecs = NSLOT <= 8 ? 160 : 192;     // staged list records
+    static constexpr int kOffRecIdx = kStageInts;
+    static constexpr int kOffRecOff = kOffRecIdx + kStageRecs;
+    static constexpr int kOffRuns = kOffRecOff + kStageRecs;      // 2 parities x (base[32], pre[32], cnt[32])
+    static constexpr int kOffQbuf = kOffRuns + 192;               // query float4[32]
+    static constexpr int kOffQr2 = kOffQbuf + 128;                // query r^2[32]
+    static constexpr int kOffCand = kOffQr2 + 32;                 // candidate float4[NSLOT*32], filled by cp.async one cell ahead
+    static constexpr bool kPipe = NSLOT <= 8;                     // cp.async candidate tiles (see query_kernel)
+    static constexpr int kOffCandR2 = kOffCand + (kPipe ? NSLOT * 32 * 4 : 0);  // candidate r^2[NSLOT*32] (symmetric variable radius only)
+    static constexpr int kWarpInts = kOffCandR2 + (kPipe && SYMMETRIC ? NSLOT * 32 : 0);
+    static constexpr int kBytes = kQueryWarps * kWarpInts * 4;
+    static constexpr int kBlocksPerSM = kBytes <= 112 * 1024 ? 2 : 1;
+    static_assert(kOffQbuf % 4 == 0 && kOffCand % 4 == 0 && kWarpInts % 4 == 0, "16-byte alignment of the float4 buffers");
+    static_assert(kStageInts >= NSLOT * 32 + 4, "the staging buffer must hold one worst-case list");
+};
 
 template <typename Key>
 struct QueryArgs {
@@ -71,13 +75,12 @@ struct QueryArgs {
 };
 
 struct WarpStage {
-    int* ints;       // [kStageInts]  staged lists  [n, j0, j1, ...]
-    int* rec_idx;    // [kStageRecs]  query index of every staged list
-    int* rec_off;    // [kStageRecs]  its offset inside ints
-    int* run_base;   // [32]          (start - prefix) of the non-empty neighbour runs, compacted
+    int* ints;       // staged lists  [n, j0, j1, ...]
+    int* rec_idx;    // query index of every staged list
+    int* rec_off;    // its offset inside ints
     int wpos;
     int nrec;
-    unsigned nb_sum;              // neighbour ids written by this warp (flushed to the 64-bit global counter before it can wrap)
+    unsigned nb_sum; // neighbour ids written by this warp (flushed to the 64-bit global counter before it can wrap)
 };
 
 // write-once data: streaming stores keep the lists from evicting the candidate tiles out of L2
@@ -112,10 +115,10 @@ __device__ __forceinline__ void stage_flush(WarpStage& st, const QueryArgs<Key>&
 // general path only: reserve room for one list of n ids whose size is already known.  Returns the destination of the count
 // word: inside the staging buffer, or -- for lists that do not fit the staging buffer at all -- directly in the ragged buffer.
 template <typename Key>
-__device__ __forceinline__ int* reserve_list(WarpStage& st, const QueryArgs<Key>& a, int lane, int qidx, int n, bool& ok)
+__device__ __forceinline__ int* reserve_list(WarpStage& st, const QueryArgs<Key>& a, int lane, int qidx, int n, int stage_ints, int stage_recs, bool& ok)
 {
     ok = true;
-    if (n + 1 > kStageInts) {
+    if (n + 1 > stage_ints) {
         const unsigned long long need = (unsigned long long)((n + 1 + 3) & ~3);
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(a.cursor, need);
@@ -133,7 +136,7 @@ __device__ __forceinline__ int* reserve_list(WarpStage& st, const QueryArgs<Key>
         if (st.nb_sum > 0x40000000u) { if (lane == 0) atomicAdd(a.n_neighbors, (unsigned long long)st.nb_sum); st.nb_sum = 0; }
         return a.ragged + base;
     }
-    if (st.wpos + n + 1 > kStageInts || st.nrec == kStageRecs) stage_flush(st, a, lane);
+    if (st.wpos + n + 1 > stage_ints || st.nrec == stage_recs) stage_flush(st, a, lane);
     int* dst = st.ints + st.wpos;
     if (lane == 0) {
         dst[0] = n;
@@ -178,8 +181,7 @@ __device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi)
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
 // x + (-0.0) == x for every x: an exact identity that ptxas cannot fold away, used once per cell to make the candidate
-// pairs live in aligned 64-bit registers (otherwise the halves stay in the LDG.128 destination registers and every FADD2 of
-// the inner loop needs two extra moves to assemble its operand).
+// pairs live in aligned 64-bit registers (otherwise every FADD2 of the inner loop needs two extra moves for its operand).
 __device__ __forceinline__ f32x2 settle2(f32x2 a)
 {
     f32x2 r;
@@ -205,120 +207,174 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
     return r;
 }
 
-// The dense candidate list of a cell is the concatenation of its (up to 27) non-empty neighbour runs.  RunTable answers
-// "which position of the sorted array is candidate t" for the 32 consecutive candidates of one slot with one REDUX.OR,
-// one VOTE and a popc per lane (no per-lane search): bit b of `starts` says that a run begins at candidate base+b.
-struct RunTable {
-    int pre;         // this lane's run: first candidate number (exclusive prefix of the run lengths)
-    int cnt;         // this lane's run: length (0 = no run on this lane)
-    const int* run_base;
-    __device__ __forceinline__ int pos(int slot_base, int lane) const
-    {
-        const bool starts_here = cnt > 0 && pre >= slot_base && pre < slot_base + 32;
-        const unsigned starts = __reduce_or_sync(kFull, starts_here ? (1u << (pre - slot_base)) : 0u);
-        const int before = __popc(__ballot_sync(kFull, cnt > 0 && pre < slot_base));
-        const int k = before + __popc(starts & (0xffffffffu >> (31 - lane))) - 1;
-        return run_base[max(k, 0)] + slot_base + lane;
-    }
-};
+// asynchronous global -> shared copies (LDGSTS): the data never passes through registers, so a warp can have the whole
+// candidate tile of its NEXT cell in flight while its registers still hold the current one
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// The dense candidate list of a cell is the concatenation of its (up to 27) non-empty neighbour runs.  For the 32
+// consecutive candidates of one slot, "which position of the sorted array is candidate t" is answered with one REDUX.OR,
+// one VOTE and a popc per lane (no per-lane search): bit b of `starts` says that a run begins at candidate slot_base+b.
+// pre / cnt: this lane's run (first candidate number, length); run_base[k] = start - pre of the k-th non-empty run.
+__device__ __forceinline__ int candidate_pos(int pre, int cnt, const int* run_base, int slot_base, int lane)
+{
+    const bool starts_here = cnt > 0 && pre >= slot_base && pre < slot_base + 32;
+    const unsigned starts = __reduce_or_sync(kFull, starts_here ? (1u << (pre - slot_base)) : 0u);
+    const int before = __popc(__ballot_sync(kFull, cnt > 0 && pre < slot_base));
+    const int k = before + __popc(starts & (0xffffffffu >> (31 - lane))) - 1;
+    return run_base[max(k, 0)] + slot_base + lane;
+}
 
 template <typename Key, int NSLOT, bool VARIABLE, bool SYMMETRIC, bool DENSE>
-__global__ void __launch_bounds__(kQueryThreads, NSLOT <= 8 ? kQueryBlocksPerSM : 2) query_kernel(const QueryArgs<Key> a)
+__global__ void __launch_bounds__(kQueryThreads, QLayout<NSLOT, SYMMETRIC>::kBlocksPerSM) query_kernel(const QueryArgs<Key> a)
 {
+    typedef QLayout<NSLOT, SYMMETRIC> LO;
     static_assert(NSLOT % 2 == 0, "slots are processed in packed pairs");
+    // The cp.async tile pipeline costs a few live registers; the 16-slot variant (dense clouds, 64 candidate registers) is
+    // already at the 128-register limit of 2 CTAs/SM and keeps the direct global -> register loads instead.
+    constexpr bool PIPE = NSLOT <= 8;
     extern __shared__ __align__(16) int s_mem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int* const wmem = s_mem + warp * LO::kWarpInts;
     WarpStage st;
-    st.ints = s_mem + warp * kWarpSmemInts;
-    st.rec_idx = st.ints + kOffRecIdx;
-    st.rec_off = st.ints + kOffRecOff;
-    st.run_base = st.ints + kOffRunStart;
-    float4* qbuf = reinterpret_cast<float4*>(st.ints + kOffQbuf);
-    float* qr2s = reinterpret_cast<float*>(st.ints + kOffQr2);
+    st.ints = wmem;
+    st.rec_idx = wmem + LO::kOffRecIdx;
+    st.rec_off = wmem + LO::kOffRecOff;
     st.wpos = 0;
     st.nrec = 0;
     st.nb_sum = 0;
+    int* const runs = wmem + LO::kOffRuns;                    // [parity][base | pre | cnt][32]
+    float4* const qbuf = reinterpret_cast<float4*>(wmem + LO::kOffQbuf);
+    float* const qr2s = reinterpret_cast<float*>(wmem + LO::kOffQr2);
+    float4* const cand = reinterpret_cast<float4*>(wmem + LO::kOffCand);
+    float* const cand_r2 = reinterpret_cast<float*>(wmem + LO::kOffCandR2);
 
     const uint32_t hmask = (1u << a.hash_log2) - 1u;
     const unsigned lt = lanemask_lt();
     const float r2_fixed = a.r2_fixed;
     const int query_limit = a.query_limit;
     const bool same_set = a.same_set != 0;
+    const uint32_t n_cells = (uint32_t)a.n_q_cells;
 
-    for (;;) {
-        uint32_t c0 = 0;
-        if (lane == 0) c0 = atomicAdd(a.ticket, (uint32_t)kCellsPerTicket);
-        c0 = __shfl_sync(kFull, c0, 0);
-        if (c0 >= (uint32_t)a.n_q_cells) break;
-        const uint32_t c1 = min(c0 + (uint32_t)kCellsPerTicket, (uint32_t)a.n_q_cells);
-
-        // The batch's cell keys and query ranges arrive with ONE coalesced load per array (lanes 0..16), cells then read them by shuffle.
-        const uint32_t nb = c1 - c0;
-        Key my_key = 0;
-        int my_start = 0;
-        if ((uint32_t)lane < nb) my_key = a.q_cell_key[c0 + lane];
-        if ((uint32_t)lane <= nb) my_start = (int)a.q_cell_start[c0 + lane];
-
-        // Software pipeline over the cells of the batch: the neighbour lookup of cell c+1 is issued before the queries of cell c are
-        // processed, so its memory round trip is hidden behind that work (the lookup is ONE vector load per neighbour cell).
-        Key nkey_next = 0;
-        uint32_t slot_next = 0;
-        bool valid_next = false;
-        typename HashSlot<Key>::Raw e_next;
-        uint2 d_next = make_uint2(0u, 0u);
-        auto issue_lookup = [&](uint32_t i) {
-            const Key key = __shfl_sync(kFull, my_key, (int)i);
-            // neighbour cell offset owned by this lane (lanes 27..31 idle during the lookup).  The opaque copy of the lane id
-            // keeps the per-lane Morton constants from being hoisted out of the cell loop (they would cost ~10 registers).
-            int l = lane;
-            asm volatile("" : "+r"(l));
-            const int ox = l % 3 - 1, oy = (l / 3) % 3 - 1, oz = l / 9 - 1;
-            valid_next = l < 27;
-            nkey_next = morton_neighbor<Key>(key, ox, oy, oz, a.key_mask, valid_next);
-            if (DENSE) {
-                d_next = make_uint2(0u, 0u);
-                if (valid_next) d_next = __ldg(a.dense + nkey_next);
-            } else {
-                slot_next = Morton<Key>::hash(nkey_next) >> (32 - a.hash_log2);
-                if (valid_next) e_next = HashSlot<Key>::load(a.htable, slot_next);
+    // ---- neighbour lookup of one cell, split in "issue" (no waiting) and "resolve" (waits for the load issued earlier)
+    Key lk_key = 0;
+    uint32_t lk_slot = 0;
+    bool lk_valid = false;
+    typename HashSlot<Key>::Raw lk_e;
+    uint2 lk_d = make_uint2(0u, 0u);
+    auto issue_lookup = [&](Key cell_key) {
+        // neighbour cell offset owned by this lane (lanes 27..31 idle during the lookup).  The opaque copy of the lane id
+        // keeps the per-lane Morton constants from being hoisted out of the cell loop.
+        int l = lane;
+        asm volatile("" : "+r"(l));
+        const int ox = l % 3 - 1, oy = (l / 3) % 3 - 1, oz = l / 9 - 1;
+        lk_valid = l < 27;
+        lk_key = morton_neighbor<Key>(cell_key, ox, oy, oz, a.key_mask, lk_valid);
+        if (DENSE) {
+            lk_d = make_uint2(0u, 0u);
+            if (lk_valid) lk_d = __ldg(a.dense + lk_key);
+        } else {
+            lk_slot = Morton<Key>::hash(lk_key) >> (32 - a.hash_log2);
+            if (lk_valid) lk_e = HashSlot<Key>::load(a.htable, lk_slot);
+        }
+    };
+    // resolve the pending lookup into the run table of `parity`, start the asynchronous copy of the candidates into shared
+    // memory, return T (candidate count) and the first candidate number of the cell's own run
+    auto resolve_and_stage = [&](int parity, int& T_out, int& self_pre_out) {
+        int rs = 0, rc = 0;
+        if (DENSE) {
+            rs = (int)lk_d.x;
+            rc = (int)(lk_d.y - lk_d.x);
+        } else if (lk_valid) {
+            typename HashSlot<Key>::Raw e = lk_e;
+            uint32_t slot = lk_slot;
+            for (;;) {
+                if (HashSlot<Key>::matches(e, lk_key)) { rs = HashSlot<Key>::start(e); rc = HashSlot<Key>::count(e); break; }
+                if (HashSlot<Key>::is_empty(e)) break;
+                slot = (slot + 1) & hmask;
+                e = HashSlot<Key>::load(a.htable, slot);
             }
-        };
-        issue_lookup(0);
-
-        for (uint32_t i = 0; i < nb; i++) {
-            // ---------------- the 27 neighbour runs of this cell: resolve the lookup issued one iteration ago
-            const int qb = __shfl_sync(kFull, my_start, (int)i), qe = __shfl_sync(kFull, my_start, (int)i + 1);
-            int rs = 0, rc = 0;
-            if (DENSE) {
-                rs = (int)d_next.x;
-                rc = (int)(d_next.y - d_next.x);
-            } else if (valid_next) {
-                typename HashSlot<Key>::Raw e = e_next;
-                uint32_t slot = slot_next;
-                for (;;) {
-                    if (HashSlot<Key>::matches(e, nkey_next)) { rs = HashSlot<Key>::start(e); rc = HashSlot<Key>::count(e); break; }
-                    if (HashSlot<Key>::is_empty(e)) break;
-                    slot = (slot + 1) & hmask;
-                    e = HashSlot<Key>::load(a.htable, slot);
+        }
+        const int inc = warp_inclusive_scan(rc, lane);
+        const int T = __shfl_sync(kFull, inc, 31);
+        const int pre = inc - rc;
+        int* rb = runs + parity * 96;
+        const unsigned nonempty = __ballot_sync(kFull, rc > 0);
+        if (rc > 0) rb[__popc(nonempty & lt)] = rs - pre;
+        rb[32 + lane] = pre;
+        rb[64 + lane] = rc;
+        __syncwarp();
+        if (PIPE && T <= NSLOT * 32) {
+#pragma unroll
+            for (int s = 0; s < NSLOT; s++) {
+                if (s * 32 < T) {
+                    const int pos = candidate_pos(pre, rc, rb, s * 32, lane);
+                    if (s * 32 + lane < T) {
+                        cp_async_16(cand + s * 32 + lane, a.c_pts + pos);
+                        if (SYMMETRIC) cp_async_4(cand_r2 + s * 32 + lane, a.c_r2 + pos);
+                    }
                 }
             }
-            if (i + 1 < nb) issue_lookup(i + 1);
-            const int inc = warp_inclusive_scan(rc, lane);
-            const int T = __shfl_sync(kFull, inc, 31);
-            RunTable runs;
-            runs.pre = inc - rc;
-            runs.cnt = rc;
-            runs.run_base = st.run_base;
-            {
-                const unsigned nonempty = __ballot_sync(kFull, rc > 0);
-                __syncwarp();
-                if (rc > 0) st.run_base[__popc(nonempty & lt)] = rs - runs.pre;
-                __syncwarp();
-            }
-            const int self_pre = __shfl_sync(kFull, runs.pre, 13);   // lane 13 = offset (0,0,0): the cell itself when same_set
+        }
+        if (PIPE) cp_async_commit();
+        T_out = T;
+        self_pre_out = __shfl_sync(kFull, pre, 13);           // lane 13 = offset (0,0,0): the cell itself when same_set
+    };
 
+    // ---- batches of consecutive cells from the ticket counter; the next ticket and the next batch's keys are prefetched
+    uint32_t c0 = 0;
+    if (lane == 0) c0 = atomicAdd(a.ticket, (uint32_t)kCellsPerTicket);
+    c0 = __shfl_sync(kFull, c0, 0);
+    Key my_key = 0;
+    int my_start = 0;
+    if (c0 < n_cells) {
+        if (c0 + lane < n_cells) my_key = a.q_cell_key[c0 + lane];
+        if (c0 + lane <= n_cells) my_start = (int)a.q_cell_start[c0 + lane];
+    }
+
+    while (c0 < n_cells) {
+        const int nb = (int)min((uint32_t)kCellsPerTicket, n_cells - c0);
+        uint32_t t_next = 0;
+        if (PIPE && lane == 0) t_next = atomicAdd(a.ticket, (uint32_t)kCellsPerTicket);     // consumed half a batch later
+        Key next_key = 0;
+        int next_start = 0;
+        uint32_t c0_next = 0xffffffffu;
+
+        int T_cur = 0, self_cur = 0;
+        issue_lookup(__shfl_sync(kFull, my_key, 0));
+
+        for (int i = 0; i < nb; i++) {
+            // PIPE: cell i was resolved and its tile copy started one iteration ago (cell 0: here, the pipeline prologue).
+            // !PIPE: every cell is resolved here; only its lookup was issued one iteration ago.
+            if (!PIPE || i == 0) {
+                resolve_and_stage(i & 1, T_cur, self_cur);
+                if (i + 1 < nb) issue_lookup(__shfl_sync(kFull, my_key, i + 1));
+            }
+            const int T = T_cur, self_pre = self_cur;
+            const int qb = __shfl_sync(kFull, my_start, i), qe = __shfl_sync(kFull, my_start, i + 1);
+            const int* rb = runs + (i & 1) * 96;
+
+            if (PIPE && i == (nb >> 1)) {
+                // prefetch the next batch's keys / query ranges (the ticket requested at the batch start has arrived by now)
+                c0_next = __shfl_sync(kFull, t_next, 0);
+                if (c0_next < n_cells) {
+                    if (c0_next + lane < n_cells) next_key = a.q_cell_key[c0_next + lane];
+                    if (c0_next + lane <= n_cells) next_start = (int)a.q_cell_start[c0_next + lane];
+                }
+            }
+
+            if (PIPE) cp_async_wait_all();
+            __syncwarp();
             if (T <= NSLOT * 32) {
-                // ---------------- fast path: the whole candidate list lives in registers, two slots per packed register
+                // ---------------- fast path: the candidate tile moves from shared memory to registers, two slots per packed register
                 f32x2 px[NSLOT / 2], py[NSLOT / 2], pz[NSLOT / 2];
                 int pid[NSLOT];
                 float pr2[SYMMETRIC ? NSLOT : 1];
@@ -327,18 +383,30 @@ __global__ void __launch_bounds__(kQueryThreads, NSLOT <= 8 ? kQueryBlocksPerSM 
                     // a lane without a candidate holds a point at x = 3e38: d2 = inf, never a hit (and r2 = -1 for the symmetric test)
                     float4 v0 = make_float4(3.0e38f, 0.0f, 0.0f, __int_as_float(-1)), v1 = v0;
                     float w0 = -1.0f, w1 = -1.0f;
-                    if (2 * j * 32 < T) {
-                        const int pos = runs.pos(2 * j * 32, lane);
+                    if (PIPE) {
                         if (2 * j * 32 + lane < T) {
-                            v0 = a.c_pts[pos];
-                            if (SYMMETRIC) w0 = a.c_r2[pos];
+                            v0 = cand[2 * j * 32 + lane];
+                            if (SYMMETRIC) w0 = cand_r2[2 * j * 32 + lane];
                         }
-                    }
-                    if ((2 * j + 1) * 32 < T) {
-                        const int pos = runs.pos((2 * j + 1) * 32, lane);
                         if ((2 * j + 1) * 32 + lane < T) {
-                            v1 = a.c_pts[pos];
-                            if (SYMMETRIC) w1 = a.c_r2[pos];
+                            v1 = cand[(2 * j + 1) * 32 + lane];
+                            if (SYMMETRIC) w1 = cand_r2[(2 * j + 1) * 32 + lane];
+                        }
+                    } else {
+                        const int pre = rb[32 + lane], cnt = rb[64 + lane];
+                        if (2 * j * 32 < T) {
+                            const int pos = candidate_pos(pre, cnt, rb, 2 * j * 32, lane);
+                            if (2 * j * 32 + lane < T) {
+                                v0 = a.c_pts[pos];
+                                if (SYMMETRIC) w0 = a.c_r2[pos];
+                            }
+                        }
+                        if ((2 * j + 1) * 32 < T) {
+                            const int pos = candidate_pos(pre, cnt, rb, (2 * j + 1) * 32, lane);
+                            if ((2 * j + 1) * 32 + lane < T) {
+                                v1 = a.c_pts[pos];
+                                if (SYMMETRIC) w1 = a.c_r2[pos];
+                            }
                         }
                     }
                     px[j] = settle2(pack2(v0.x, v1.x));
@@ -348,16 +416,23 @@ __global__ void __launch_bounds__(kQueryThreads, NSLOT <= 8 ? kQueryBlocksPerSM 
                     pid[2 * j + 1] = __float_as_int(v1.w);
                     if (SYMMETRIC) { pr2[2 * j] = w0; pr2[2 * j + 1] = w1; }
                 }
+                if (PIPE) {
+                    __syncwarp();      // every lane has read its candidates: the tile buffer may be refilled
+                    // next cell: resolve its lookup, start the copy of its candidate tile, put the lookup after it in flight
+                    if (i + 1 < nb) {
+                        resolve_and_stage((i + 1) & 1, T_cur, self_cur);
+                        if (i + 2 < nb) issue_lookup(__shfl_sync(kFull, my_key, i + 2));
+                    }
+                }
+
                 // number of packed slot pairs in use; the query loop is instantiated per count so that its body is straight-line.
-                // It returns early when the staging buffer cannot take another worst-case list; the flush lives in ONE place
-                // outside the specialised loops (inlining it into each of them costs registers in the hot loop).
-                // (the 16-slot variant only instantiates 2, 4, 6 and 8 pairs; unused pairs hold far-away points)
+                // It returns early when the staging buffer cannot take another worst-case list; the flush lives in ONE place.
                 const int npairs_exact = max((T + 63) >> 6, 1);
                 const int npairs = NSLOT == 8 ? npairs_exact : min((npairs_exact + 1) & ~1, NSLOT / 2);
                 auto run_queries = [&](auto np_tag, int k, const int nq, const int q0) -> int {
                     constexpr int NP = decltype(np_tag)::value;
                     for (; k < nq; k++) {
-                        if (st.wpos + 1 + NP * 64 > kStageInts || st.nrec == kStageRecs) return k;
+                        if (st.wpos + 1 + NP * 64 > LO::kStageInts || st.nrec == LO::kStageRecs) return k;
                         const float4 q = qbuf[k];
                         const int qidx = __float_as_int(q.w);
                         if (qidx >= query_limit) continue;
@@ -407,7 +482,7 @@ __global__ void __launch_bounds__(kQueryThreads, NSLOT <= 8 ? kQueryBlocksPerSM 
                     const int nq = min(32, qe - q0);
                     int k = 0;
                     while (k < nq) {
-                        if (st.wpos + 1 + npairs * 64 > kStageInts || st.nrec == kStageRecs) stage_flush(st, a, lane);
+                        if (st.wpos + 1 + npairs * 64 > LO::kStageInts || st.nrec == LO::kStageRecs) stage_flush(st, a, lane);
                         if (NSLOT == 8) {
                             switch (npairs) {
                             case 1: k = run_queries(std::integral_constant<int, 1>{}, k, nq, q0); break;
@@ -426,7 +501,13 @@ __global__ void __launch_bounds__(kQueryThreads, NSLOT <= 8 ? kQueryBlocksPerSM 
                     }
                 }
             } else {
-                // ---------------- general path (very dense neighbourhoods): two sweeps per query, candidates re-read through L1
+                // ---------------- general path (very dense neighbourhoods): two sweeps per query, candidates re-read through L1/L2.
+                // The run table of this cell stays valid in its parity slot while the next cell is resolved into the other one.
+                if (PIPE && i + 1 < nb) {
+                    resolve_and_stage((i + 1) & 1, T_cur, self_cur);
+                    if (i + 2 < nb) issue_lookup(__shfl_sync(kFull, my_key, i + 2));
+                }
+                const int pre = rb[32 + lane], cnt = rb[64 + lane];
                 for (int qi = qb; qi < qe; qi++) {
                     const float4 qv = a.q_pts[qi];
                     const int qidx = __float_as_int(qv.w);
@@ -436,7 +517,7 @@ __global__ void __launch_bounds__(kQueryThreads, NSLOT <= 8 ? kQueryBlocksPerSM 
                     int n = 0;
                     for (int t0 = 0; t0 < T; t0 += 32) {
                         const int t = t0 + lane;
-                        const int pos = runs.pos(t0, lane);
+                        const int pos = candidate_pos(pre, cnt, rb, t0, lane);
                         bool h = false;
                         if (t < T && t != ts) {
                             const float4 v = a.c_pts[pos];
@@ -447,12 +528,12 @@ __global__ void __launch_bounds__(kQueryThreads, NSLOT <= 8 ? kQueryBlocksPerSM 
                         n += __popc(__ballot_sync(kFull, h));
                     }
                     bool ok;
-                    int* dst = reserve_list(st, a, lane, qidx, n, ok);
+                    int* dst = reserve_list(st, a, lane, qidx, n, LO::kStageInts, LO::kStageRecs, ok);
                     if (!ok) continue;
                     int p = 1;
                     for (int t0 = 0; t0 < T; t0 += 32) {
                         const int t = t0 + lane;
-                        const int pos = runs.pos(t0, lane);
+                        const int pos = candidate_pos(pre, cnt, rb, t0, lane);
                         bool h = false;
                         int id = -1;
                         if (t < T && t != ts) {
@@ -467,6 +548,22 @@ __global__ void __launch_bounds__(kQueryThreads, NSLOT <= 8 ? kQueryBlocksPerSM 
                         p += __popc(m);
                     }
                 }
+            }
+        }
+        // next batch (its keys were prefetched half a batch ago)
+        if (PIPE) {
+            c0 = c0_next;
+            my_key = next_key;
+            my_start = next_start;
+        } else {
+            // the register-tight 16-slot variant fetches the next batch synchronously
+            if (lane == 0) t_next = atomicAdd(a.ticket, (uint32_t)kCellsPerTicket);
+            c0 = __shfl_sync(kFull, t_next, 0);
+            my_key = 0;
+            my_start = 0;
+            if (c0 < n_cells) {
+                if (c0 + lane < n_cells) my_key = a.q_cell_key[c0 + lane];
+                if (c0 + lane <= n_cells) my_start = (int)a.q_cell_start[c0 + lane];
             }
         }
     }

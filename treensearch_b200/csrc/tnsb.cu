@@ -332,12 +332,15 @@ int build_sets(tnsb_context* c, const GridParams& gp)
 }
 
 template <typename Key, int NSLOT, bool DENSE>
-cudaError_t launch_query(const QueryArgs<Key>& a, bool variable, bool symmetric, int grid, cudaStream_t s)
+cudaError_t launch_query(const QueryArgs<Key>& a, bool variable, bool symmetric, int n_sms, cudaStream_t s)
 {
+    // persistent CTAs: as many as fit per SM for this instantiation's shared memory footprint
+    const int smem = symmetric ? QLayout<NSLOT, true>::kBytes : QLayout<NSLOT, false>::kBytes;
+    const int grid = n_sms * (symmetric ? QLayout<NSLOT, true>::kBlocksPerSM : QLayout<NSLOT, false>::kBlocksPerSM);
     auto go = [&](auto kernel) -> cudaError_t {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQuerySmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        kernel<<<grid, kQueryThreads, kQuerySmemBytes, s>>>(a);
+        kernel<<<grid, kQueryThreads, smem, s>>>(a);
         return cudaGetLastError();
     };
     if (!variable) return go(query_kernel<Key, NSLOT, false, false, DENSE>);
@@ -377,7 +380,7 @@ int query_pair(tnsb_context* c, int si, int sj, const GridParams& gp, PairCounte
     const bool symmetric = variable && c->symmetric;   // TreeNSearch.cpp:2431
     // register slots for the candidate list: 27 cells of average population
     const double avg_cell = cj.n_cells > 0 ? (double)cj.n / cj.n_cells : 0.0;
-    const int grid = kQueryBlocksPerSM * c->n_sms;
+    const int grid = c->n_sms;
     cudaError_t e;
     const bool small = 27.0 * avg_cell * 1.15 <= 256.0;
     if (cj.use_dense) e = small ? launch_query<Key, 8, true>(a, variable, symmetric, grid, c->stream) : launch_query<Key, 16, true>(a, variable, symmetric, grid, c->stream);
