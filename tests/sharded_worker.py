@@ -15,19 +15,16 @@ from oracle import loader  # noqa: E402
 from treensearch_b200 import clouds, sharded  # noqa: E402
 
 
-def main():
-    rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local_rank)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    n_total = 200_000
-    cloud = clouds.uniform_cloud(n_total, 77)
-    cloud[:, 2] = cloud[:, 2] ** 1.5
-    r = float(clouds.radius_for_mean_neighbors(n_total, 25.0))
+def scenario(rank, world, local_rank, n_total, k_mean, seed, power, radius=None):
+    cloud = clouds.uniform_cloud(n_total, seed)
+    cloud[:, 2] = cloud[:, 2] ** power
+    r = float(clouds.radius_for_mean_neighbors(n_total, k_mean)) if radius is None else radius
     per = n_total // world
     chunk = torch.from_numpy(np.ascontiguousarray(cloud[rank * per:(rank + 1) * per])).cuda()
     search = sharded.ShardedSearch(r, rank, world, local_rank, stream=torch.cuda.current_stream(), dist=dist)
-    for _ in range(2):                                   # second step reuses buffers (resize path)
+    for _ in range(3):                                   # later steps reuse buffers and (balanced) cuts
         search.step(chunk, rank * per)
+    assert search.n_recuts <= 2, "balanced cuts should have been reused"
     mine = search.owned_lists_global()
     port = loader.OraclePort()
     port.set_search_radius(r)
@@ -40,8 +37,19 @@ def main():
     counts = torch.tensor([len(mine)], device="cuda")
     dist.all_reduce(counts)
     assert int(counts.item()) == n_total, "owned points do not partition the cloud"
+    return len(mine), search.n_halo
+
+
+def main():
+    rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    owned, halo = scenario(rank, world, local_rank, 200_000, 25.0, 77, 1.5)
+    # slabs thinner than the halo: points are replicated to several ranks and the record buffer has to grow
+    owned2, halo2 = scenario(rank, world, local_rank, 4_000, 0.0, 78, 1.0, radius=0.6 / world + 0.15)
+    assert halo2 > 0
     if rank == 0:
-        print(f"SHARDED_OK world={world} owned={len(mine)} halo={search.n_halo}")
+        print(f"SHARDED_OK world={world} owned={owned} halo={halo} | thin slabs: owned={owned2} halo={halo2}")
     dist.destroy_process_group()
 
 

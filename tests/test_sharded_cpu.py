@@ -52,7 +52,8 @@ def _worker(rank, world, port, out_dir):
         cuts = sharded.balanced_cuts(hist.numpy(), lo, hi, world)
         halo = sharded.halo_width(RADIUS)
         records, counts = partition_numpy(chunk, rank * per, axis, cuts, halo, world)
-        local, n_owned, n_halo = sharded.exchange_records(dist, torch.from_numpy(records), counts, world)
+        local, n_owned, n_halo, flag = sharded.exchange_records(dist, torch.from_numpy(records), counts, world, flag=rank)
+        assert flag == world - 1                       # the flag that rides on the counts exchange: max over ranks
         local = local.numpy()
         # owned counts are balanced and partition the cloud
         tot = torch.tensor([n_owned, n_halo])
@@ -118,5 +119,5 @@ def test_balanced_cuts_properties():
 def test_single_rank_exchange_is_identity():
     rec = torch.arange(40, dtype=torch.float32).reshape(10, 4)
     counts = np.array([7, 3], dtype=np.int64)
-    local, n_owned, n_halo = sharded.exchange_records(None, rec, counts, 1)
-    assert n_owned == 7 and n_halo == 3 and torch.equal(local, rec)
+    local, n_owned, n_halo, flag = sharded.exchange_records(None, rec, counts, 1, flag=5)
+    assert n_owned == 7 and n_halo == 3 and flag == 5 and torch.equal(local, rec)

@@ -52,18 +52,22 @@ def halo_width(r_max: float) -> np.float32:
     return np.float32(np.float32(r_max) * np.float32(1.0 + 1.0 / 1024.0))
 
 
-def exchange_records(dist, records, counts: np.ndarray, world: int):
+def exchange_records(dist, records, counts: np.ndarray, world: int, flag: int = 0):
     """Step 4.  `records` is a torch tensor [total, 4] laid out as the partition produced it; counts = int64[2*world]
-    (owned counts then halo counts, per destination).  Returns (local [n_owned + n_halo, 4], n_owned, n_halo)."""
+    (owned counts then halo counts, per destination).  `flag` is one extra integer every rank tells every other rank in the
+    same (small) counts exchange; the maximum over ranks comes back.
+    Returns (local [n_owned + n_halo, 4], n_owned, n_halo, max_flag)."""
     import torch
     dev = records.device
-    send_counts = torch.from_numpy(np.ascontiguousarray(counts.reshape(2, world).T)).to(dev)     # [dest, kind]
+    sc = np.empty((world, 3), dtype=np.int64)                 # [dest, (owned, halo, flag)]
+    sc[:, 0], sc[:, 1], sc[:, 2] = counts[:world], counts[world:], flag
+    send_counts = torch.from_numpy(sc).to(dev)
     recv_counts = torch.empty_like(send_counts)
     if world > 1:
         dist.all_to_all_single(recv_counts, send_counts)
     else:
         recv_counts.copy_(send_counts)
-    rc = recv_counts.cpu().numpy()                      # [source, kind]
+    rc = recv_counts.cpu().numpy()                      # [source, (owned, halo, flag)]
     own_in, halo_in = rc[:, 0].astype(np.int64), rc[:, 1].astype(np.int64)
     own_out, halo_out = counts[:world].astype(np.int64), counts[world:].astype(np.int64)
     n_owned, n_halo = int(own_in.sum()), int(halo_in.sum())
@@ -76,7 +80,7 @@ def exchange_records(dist, records, counts: np.ndarray, world: int):
     else:
         local[:n_owned].copy_(owned_src)
         local[n_owned:].copy_(halo_src)
-    return local, n_owned, n_halo
+    return local, n_owned, n_halo, int(rc[:, 2].max())
 
 
 class ShardedSearch:
@@ -102,6 +106,12 @@ class ShardedSearch:
         self.local = None
         self.n_owned = self.n_halo = 0
         self.cuts = None
+        # temporal coherence: the cuts of the previous step are kept while every rank's owned count stays within
+        # `rebalance_tolerance` of the mean; any rank can request new cuts through the flag that rides on the counts exchange
+        self.rebalance_tolerance = 0.10
+        self.n_global = 0
+        self._recut = True
+        self.n_recuts = 0
 
     # ---- thin wrappers of the shard helpers of the C ABI
     def _aabb(self, pts):
@@ -120,29 +130,45 @@ class ShardedSearch:
             self._records = torch.empty((need, 4), dtype=torch.float32, device=self.device)
         counts = (C.c_int64 * (2 * self.world))()
         cuts_c = (C.c_float * (self.world + 1))(*[float(c) if np.isfinite(c) else 0.0 for c in cuts])
-        self.engine._check(self.engine._lib.tnsb_shard_partition(self.engine._h, pts.data_ptr(), pts.shape[0], pts.shape[1], int(id_base), self.axis,
-                                                                cuts_c, self.world, float(halo), self._records.data_ptr(), self._records.shape[0], counts))
+        for _attempt in range(2):
+            rc = self.engine._lib.tnsb_shard_partition(self.engine._h, pts.data_ptr(), pts.shape[0], pts.shape[1], int(id_base), self.axis,
+                                                      cuts_c, self.world, float(halo), self._records.data_ptr(), self._records.shape[0], counts)
+            if rc != L.TNSB_ERR_LIMIT:
+                break
+            # thin slabs (halo wider than a slab) replicate points to several ranks: the counts are exact, grow and retry
+            need = int(sum(counts[:])) + 1024
+            self._records = torch.empty((need, 4), dtype=torch.float32, device=self.device)
+        self.engine._check(rc)
         return np.array(counts[:], dtype=np.int64)
 
     def step(self, points, id_base: int):
         """points: float32 CUDA tensor [n_local, 3] (this rank's chunk of the global cloud, ids id_base .. id_base + n_local)."""
         torch, dist = self.torch, self.dist
-        # 1. world box
-        mm = self._aabb(points)
-        box = torch.from_numpy(np.concatenate([-mm[:3], mm[3:]])).to(self.device)
-        if self.world > 1:
-            dist.all_reduce(box, op=dist.ReduceOp.MAX)
-        box = box.cpu().numpy()
-        lo, hi = -box[self.axis], box[3 + self.axis]
-        hi = hi + max(1e-6 * abs(hi - lo), 1e-30)
-        # 2. balanced cuts
-        self._histogram(points, lo, hi)
-        if self.world > 1:
-            dist.all_reduce(self._hist, op=dist.ReduceOp.SUM)
-        self.cuts = balanced_cuts(self._hist.cpu().numpy(), lo, hi, self.world)
-        # 3. partition, 4. exchange
+        if self._recut or self.cuts is None:
+            # 1. world box
+            mm = self._aabb(points)
+            box = torch.from_numpy(np.concatenate([-mm[:3], mm[3:]])).to(self.device)
+            if self.world > 1:
+                dist.all_reduce(box, op=dist.ReduceOp.MAX)
+            box = box.cpu().numpy()
+            lo, hi = -box[self.axis], box[3 + self.axis]
+            hi = hi + max(1e-6 * abs(hi - lo), 1e-30)
+            # 2. balanced cuts
+            self._histogram(points, lo, hi)
+            if self.world > 1:
+                dist.all_reduce(self._hist, op=dist.ReduceOp.SUM)
+            hist = self._hist.cpu().numpy()
+            self.n_global = int(hist.sum())
+            self.cuts = balanced_cuts(hist, lo, hi, self.world)
+            self.n_recuts += 1
+        # 3. partition, 4. exchange (cut coordinates are open ended at both ends, so points that left the old box still have an owner)
         counts = self._partition(points, id_base, self.cuts, halo_width(self.radius))
-        self.local, self.n_owned, self.n_halo = exchange_records(dist, self._records, counts, self.world)
+        want = 0
+        if self.n_global > 0 and self.n_owned > 0:
+            mean = self.n_global / self.world
+            want = int(abs(self.n_owned - mean) > self.rebalance_tolerance * mean)     # judged on the previous step's balance
+        self.local, self.n_owned, self.n_halo, flag = exchange_records(dist, self._records, counts, self.world, want)
+        self._recut = bool(flag)
         # 5. local search, halo points find-only
         eng = self.engine
         eng.set_option(L.TNSB_OPT_QUERY_LIMIT, self.n_owned)
