@@ -278,8 +278,9 @@ def run_ours(args):
         "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, total),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(st2["h2d_bytes"]) * (1 if world == 1 else 1), "d2h_bytes_per_step": int(st2["d2h_bytes"]),
-                "note": "pinned host points in, count-prefixed neighbour lists + list_pos table copied back to pinned host memory"},
+                "h2d_bytes_per_step": int(st2["h2d_bytes"]) * world, "d2h_bytes_per_step": int(st2["d2h_bytes"]) * world,
+                "note": "pinned host points in; count-prefixed neighbour lists written by the query kernel into mapped pinned host memory "
+                        "(zero-copy, PCIe-bound) + list_pos table copied back" + ("; bytes = rank 0 x n_gpus" if world > 1 else "")},
         "gpu_launches": int(st["n_kernel_launches"]) * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "query_kernel (27-cell query)", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -319,6 +319,18 @@ def test_device_resident_io(tnsb):
     assert_matches_port(eng2, case)
 
 
+def test_zero_copy_results(tnsb):
+    # lists written by the kernel straight into mapped pinned host memory: same sets, no separate D2H of the ids
+    case = cases.GOLDEN_CASES["variable_random_sym"]()
+    eng = run_engine(tnsb, case, options={tnsb.TNSB_OPT_ZERO_COPY_RESULTS: 1})
+    assert_matches_port(eng, case)
+    eng.run()
+    assert_matches_port(eng, case)
+    eng.set_option(tnsb.TNSB_OPT_ZERO_COPY_RESULTS, 0)      # switching back re-sizes the HBM buffer
+    eng.run()
+    assert_matches_port(eng, case)
+
+
 def test_zsort_permutation_and_rerun(tnsb):
     pts = clouds.uniform_cloud(50_000, 17).copy()
     vel = np.arange(50_000, dtype=np.float32)

@@ -107,6 +107,7 @@ struct PairState {
     DevBuf d_ragged, d_list_pos;
     PinBuf h_ragged, h_list_pos;
     int64_t capacity = 0;      // ints
+    bool in_host = false;      // zero-copy mode: the query kernel wrote the lists straight into h_ragged (mapped pinned memory)
     int64_t n_ints = 0;
     int64_t n_neighbors = 0;
     int nb_min = 0, nb_max = 0;
@@ -141,6 +142,7 @@ struct tnsb_context {
     int64_t opt_list_capacity = 48;
     int64_t opt_query_limit = -1;
     bool opt_sort_lists = false;
+    bool opt_zero_copy = true;
     int opt_point_stride = 3;
 
     // world box with hysteresis (TreeNSearch.cpp:474-482)
@@ -369,7 +371,7 @@ int query_pair(tnsb_context* c, int si, int sj, const GridParams& gp, PairCounte
     a.same_set = si == sj;
     a.key_mask = (Key)(((Key)1 << (3 * gp.bits)) - 1);
     a.r2_fixed = c->radius_sq;
-    a.ragged = ps.d_ragged.as<int32_t>();
+    a.ragged = ps.in_host ? ps.h_ragged.as<int32_t>() : ps.d_ragged.as<int32_t>();
     a.capacity = ps.capacity;
     a.list_pos = ps.d_list_pos.as<long long>();
     a.cursor = &d_cnt->cursor;
@@ -550,7 +552,13 @@ int run_impl(tnsb_context* c)
         ps.valid = true;
         if (c->sets[si].n == 0 || n_total == 0) continue;
         const int64_t want = (int64_t)ps.n_lists * (c->opt_list_capacity + 1) + 4096;
-        if (ps.capacity < want) {
+        // zero-copy: the kernel's flushes go straight to mapped pinned host memory (no HBM copy of the lists, no D2H afterwards)
+        const bool in_host = c->opt_host_results && c->opt_zero_copy && !c->opt_sort_lists;
+        if (in_host != ps.in_host) { ps.in_host = in_host; ps.capacity = 0; }
+        if (ps.in_host) {
+            TNSB_CUDA(c, ps.h_ragged.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(want, ps.capacity)));
+            ps.capacity = (int64_t)(ps.h_ragged.cap / sizeof(int32_t));
+        } else if (ps.capacity < want) {
             TNSB_CUDA(c, ps.d_ragged.ensure(sizeof(int32_t) * (size_t)want));
             ps.capacity = (int64_t)(ps.d_ragged.cap / sizeof(int32_t));
         }
@@ -582,8 +590,13 @@ int run_impl(tnsb_context* c)
             if (r.overflow) {
                 // the cursor kept counting: it is the exact size needed
                 const size_t need = (size_t)((double)r.cursor * 1.1) + 4096;
-                TNSB_CUDA(c, ps.d_ragged.ensure(sizeof(int32_t) * need));
-                ps.capacity = (int64_t)(ps.d_ragged.cap / sizeof(int32_t));
+                if (ps.in_host) {
+                    TNSB_CUDA(c, ps.h_ragged.ensure(sizeof(int32_t) * need));
+                    ps.capacity = (int64_t)(ps.h_ragged.cap / sizeof(int32_t));
+                } else {
+                    TNSB_CUDA(c, ps.d_ragged.ensure(sizeof(int32_t) * need));
+                    ps.capacity = (int64_t)(ps.d_ragged.cap / sizeof(int32_t));
+                }
                 again.push_back(id);
                 c->stats.n_reruns++;
             } else {
@@ -614,9 +627,11 @@ int run_impl(tnsb_context* c)
         c->stats.n_neighbors += ps.n_neighbors;
         c->stats.n_list_ints += ps.n_ints;
         if (!c->opt_host_results || ps.n_lists == 0) continue;
-        TNSB_CUDA(c, ps.h_ragged.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(ps.n_ints, 1), 1.25));
         TNSB_CUDA(c, ps.h_list_pos.ensure(sizeof(long long) * (size_t)c->sets[si].n, 1.25));
-        TNSB_CUDA(c, cudaMemcpyAsync(ps.h_ragged.p, ps.d_ragged.p, sizeof(int32_t) * (size_t)ps.n_ints, cudaMemcpyDeviceToHost, s));
+        if (!ps.in_host) {
+            TNSB_CUDA(c, ps.h_ragged.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(ps.n_ints, 1), 1.25));
+            TNSB_CUDA(c, cudaMemcpyAsync(ps.h_ragged.p, ps.d_ragged.p, sizeof(int32_t) * (size_t)ps.n_ints, cudaMemcpyDeviceToHost, s));
+        }
         TNSB_CUDA(c, cudaMemcpyAsync(ps.h_list_pos.p, ps.d_list_pos.p, sizeof(long long) * (size_t)ps.n_lists, cudaMemcpyDeviceToHost, s));
         c->stats.d2h_bytes += (int64_t)sizeof(int32_t) * ps.n_ints + (int64_t)sizeof(long long) * ps.n_lists;
         ps.host_valid = true;
@@ -849,6 +864,7 @@ int tnsb_set_option(tnsb_context* c, int option, int64_t value)
         c->opt_list_capacity = value; return TNSB_OK;
     case TNSB_OPT_QUERY_LIMIT: c->opt_query_limit = value; return TNSB_OK;
     case TNSB_OPT_SORT_LISTS: c->opt_sort_lists = value != 0; return TNSB_OK;
+    case TNSB_OPT_ZERO_COPY_RESULTS: c->opt_zero_copy = value != 0; return TNSB_OK;
     case TNSB_OPT_POINT_STRIDE:
         if (value != 3 && value != 4) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: point stride must be 3 (xyz) or 4 (xyz + id).");
         c->opt_point_stride = (int)value; return TNSB_OK;
@@ -915,7 +931,7 @@ int tnsb_get_neighborlists_device(const tnsb_context* c, int si, int sj, const i
         return TNSB_ERR_INVALID_STATE;
     }
     const PairState& ps = c->pairs[id];
-    if (ragged) *ragged = ps.d_ragged.as<int32_t>();
+    if (ragged) *ragged = ps.in_host ? ps.h_ragged.as<int32_t>() : ps.d_ragged.as<int32_t>();   // mapped pinned memory is device addressable
     if (list_pos) *list_pos = ps.d_list_pos.as<int64_t>();
     if (n_ints) *n_ints = ps.n_ints;
     return TNSB_OK;
@@ -1077,7 +1093,7 @@ int tnsb_get_pair_neighbor_stats(const tnsb_context* c, int si, int sj, int64_t 
             h[0] = INT_MAX; h[1] = 0;
             cudaSetDevice(m->device);
             cudaMemcpyAsync(d->minmax, h, 2 * sizeof(int), cudaMemcpyHostToDevice, m->stream);
-            list_minmax_kernel<<<4 * m->n_sms, 256, 0, m->stream>>>(ps.d_ragged.as<int32_t>(), ps.d_list_pos.as<long long>(), ps.n_lists, d->minmax);
+            list_minmax_kernel<<<4 * m->n_sms, 256, 0, m->stream>>>(ps.in_host ? ps.h_ragged.as<int32_t>() : ps.d_ragged.as<int32_t>(), ps.d_list_pos.as<long long>(), ps.n_lists, d->minmax);
             cudaMemcpyAsync(h, d->minmax, 2 * sizeof(int), cudaMemcpyDeviceToHost, m->stream);
             if (cudaStreamSynchronize(m->stream) != cudaSuccess) { cudaGetLastError(); return TNSB_ERR_CUDA; }
             ps.nb_min = h[0]; ps.nb_max = h[1];
