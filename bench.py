@@ -248,9 +248,9 @@ def run_ours(args):
         sampler.start()
     ms_dev, ms_list = timed(step_dev, args.steps, max(args.warmup, 3))
     st = stats_of()
-    clocks = sampler.stop() if rank == 0 else None
     ms_e2e, _ = timed(step_e2e, max(1, min(args.steps, 5)), 3)
     st2 = stats_e2e()
+    clocks = sampler.stop() if rank == 0 else None      # sampled over both timed regions (device-resident and end-to-end)
 
     # ---- roofline of the dominant kernel (the 27-cell query): algorithmic bytes per launch / CUDA-event duration
     # query = 24 B per point + 4 B per neighbour id (read sorted xyz 12 + idx 4, write count 4 + offset 4, write k ids)
