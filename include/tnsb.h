@@ -51,6 +51,9 @@ enum {
                                     memory (PCIe writes overlap the search, no HBM copy of the ids, no D2H afterwards; measured 28.1 ms
                                     vs 29.7 ms end to end at 10M points); 0 = lists in HBM, then one D2H copy.  Ignored (HBM path) when
                                     TNSB_OPT_SORT_LISTS is set or HOST_RESULTS is 0 */
+    TNSB_OPT_QUERY_KERNEL = 8,   /* which 27-cell query kernel runs: 1 (default) = query_rounds_kernel (a lane owns a QUERY, candidate tiles in
+                                    shared memory, private hit lists), 0 = query_kernel (a lane owns a CANDIDATE, ballot compaction).
+                                    Same results; the environment variable TNSB_QUERY_KERNEL=0|1 sets the default of new contexts */
     TNSB_OPT_POINT_STRIDE = 6    /* floats between consecutive points of float32 sets: 3 (default, xyzxyz as in the reference) or
                                     4 ((x, y, z, id) records as produced by tnsb_shard_partition; the 4th word is ignored) */
 };

@@ -25,6 +25,7 @@ TNSB_OPT_QUERY_LIMIT = 4
 TNSB_OPT_SORT_LISTS = 5
 TNSB_OPT_POINT_STRIDE = 6
 TNSB_OPT_ZERO_COPY_RESULTS = 7
+TNSB_OPT_QUERY_KERNEL = 8
 
 
 class Stats(C.Structure):

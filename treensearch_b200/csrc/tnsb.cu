@@ -11,6 +11,7 @@
 #include "radix_sort.cuh"
 #include "grid_build.cuh"
 #include "query.cuh"
+#include "query_rounds.cuh"
 #include "shard.cuh"
 
 #include <algorithm>
@@ -18,6 +19,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -144,6 +146,7 @@ struct tnsb_context {
     bool opt_sort_lists = false;
     bool opt_zero_copy = true;
     int opt_point_stride = 3;
+    int opt_query_kernel = 1;      // 0: query_kernel (candidates in registers, lane = candidate), 1: query_rounds_kernel (lane = query)
 
     // world box with hysteresis (TreeNSearch.cpp:474-482)
     bool domain_valid = false;
@@ -350,6 +353,21 @@ cudaError_t launch_query(const QueryArgs<Key>& a, bool variable, bool symmetric,
     return go(query_kernel<Key, NSLOT, true, true, DENSE>);
 }
 
+template <typename Key, int NT, bool DENSE>
+cudaError_t launch_query_rounds(const QueryArgs<Key>& a, bool variable, bool symmetric, int n_sms, cudaStream_t s)
+{
+    // persistent CTAs, one per SM: every warp owns ~23 KB of shared memory (tiles + private hit lists)
+    auto go = [&](auto kernel, int smem, int threads) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        kernel<<<n_sms, threads, smem, s>>>(a);
+        return cudaGetLastError();
+    };
+    if (!variable) return go(query_rounds_kernel<Key, NT, false, false, DENSE>, RLayout<NT, false>::kBytes, RLayout<NT, false>::kThreads);
+    if (!symmetric) return go(query_rounds_kernel<Key, NT, true, false, DENSE>, RLayout<NT, false>::kBytes, RLayout<NT, false>::kThreads);
+    return go(query_rounds_kernel<Key, NT, true, true, DENSE>, RLayout<NT, true>::kBytes, RLayout<NT, true>::kThreads);
+}
+
 template <typename Key>
 int query_pair(tnsb_context* c, int si, int sj, const GridParams& gp, PairCounters* d_cnt)
 {
@@ -385,7 +403,11 @@ int query_pair(tnsb_context* c, int si, int sj, const GridParams& gp, PairCounte
     const int grid = c->n_sms;
     cudaError_t e;
     const bool small = 27.0 * avg_cell * 1.15 <= 256.0;
-    if (cj.use_dense) e = small ? launch_query<Key, 8, true>(a, variable, symmetric, grid, c->stream) : launch_query<Key, 16, true>(a, variable, symmetric, grid, c->stream);
+    if (c->opt_query_kernel == 1) {
+        // tiles of 256 candidates (4 cells per round) for the usual SPH densities, 512 (2 cells per round) for dense clouds
+        if (cj.use_dense) e = small ? launch_query_rounds<Key, 4, true>(a, variable, symmetric, grid, c->stream) : launch_query_rounds<Key, 2, true>(a, variable, symmetric, grid, c->stream);
+        else e = small ? launch_query_rounds<Key, 4, false>(a, variable, symmetric, grid, c->stream) : launch_query_rounds<Key, 2, false>(a, variable, symmetric, grid, c->stream);
+    } else if (cj.use_dense) e = small ? launch_query<Key, 8, true>(a, variable, symmetric, grid, c->stream) : launch_query<Key, 16, true>(a, variable, symmetric, grid, c->stream);
     else e = small ? launch_query<Key, 8, false>(a, variable, symmetric, grid, c->stream) : launch_query<Key, 16, false>(a, variable, symmetric, grid, c->stream);
     TNSB_CUDA(c, e);
     c->stats.n_kernel_launches++;
@@ -709,6 +731,7 @@ int tnsb_create(tnsb_context** out, int device)
         return TNSB_ERR_CUDA;
     }
     c->own_stream = c->stream;
+    if (const char* qk = getenv("TNSB_QUERY_KERNEL")) c->opt_query_kernel = (qk[0] == '0') ? 0 : 1;      // A/B switch for tests and profiling
     for (int k = 0; k < EV_COUNT; k++) cudaEventCreate(&c->ev[k]);
     *out = c;
     return TNSB_OK;
@@ -865,6 +888,9 @@ int tnsb_set_option(tnsb_context* c, int option, int64_t value)
     case TNSB_OPT_QUERY_LIMIT: c->opt_query_limit = value; return TNSB_OK;
     case TNSB_OPT_SORT_LISTS: c->opt_sort_lists = value != 0; return TNSB_OK;
     case TNSB_OPT_ZERO_COPY_RESULTS: c->opt_zero_copy = value != 0; return TNSB_OK;
+    case TNSB_OPT_QUERY_KERNEL:
+        if (value != 0 && value != 1) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: query kernel must be 0 (cell kernel) or 1 (round kernel).");
+        c->opt_query_kernel = (int)value; return TNSB_OK;
     case TNSB_OPT_POINT_STRIDE:
         if (value != 3 && value != 4) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: point stride must be 3 (xyz) or 4 (xyz + id).");
         c->opt_point_stride = (int)value; return TNSB_OK;
