@@ -71,8 +71,9 @@ __global__ void __launch_bounds__(kAabbThreads) aabb_kernel(const T* __restrict_
 
 // ----------------------------------------------------------------------------------------------------------------------
 // Cell assignment + Morton key.  ijk = floor((p - bottom) * inv_cell) like TreeNSearch.cpp:713-715, but in fp64 and clamped.
+// row_order = 0: 3-D Morton keys (libmorton order); 1: row keys (x consecutive inside a (y, z) row, common.cuh RowKey).
 template <typename Key>
-__global__ void __launch_bounds__(256) keygen_kernel(const float* __restrict__ pts, int n, int stride, GridParams g, Key* __restrict__ keys)
+__global__ void __launch_bounds__(256) keygen_kernel(const float* __restrict__ pts, int n, int stride, GridParams g, Key* __restrict__ keys, int row_order)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(256) keygen_kernel(const float* __restrict__ p
     cx = min(max(cx, 0), g.max_coord);
     cy = min(max(cy, 0), g.max_coord);
     cz = min(max(cz, 0), g.max_coord);
-    keys[i] = Morton<Key>::encode((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+    keys[i] = row_order ? RowKey<Key>::encode((uint32_t)cx, (uint32_t)cy, (uint32_t)cz, g.bits) : Morton<Key>::encode((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
 }
 
 // ----------------------------------------------------------------------------------------------------------------------
@@ -195,6 +196,17 @@ __global__ void __launch_bounds__(256) dense_table_kernel(const Key* __restrict_
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_cells) return;
     table[cell_key[c]] = fill ? make_uint2(cell_start[c], cell_start[c + 1]) : make_uint2(0u, 0u);
+}
+
+// prefix cell table, step 1: population of every occupied cell at table[key] (the table was zeroed); an exclusive scan then turns
+// it into first[key] = number of points with a smaller key, valid for EVERY key in [0, 2^key_bits] (empty cells included)
+template <typename Key>
+__global__ void __launch_bounds__(256) cell_population_kernel(const Key* __restrict__ cell_key, const uint32_t* __restrict__ cell_start, int n_cells,
+                                                              uint32_t* __restrict__ table)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    table[cell_key[c]] = cell_start[c + 1] - cell_start[c];
 }
 
 // gather used by tnsb_apply_zsort_device_f32

@@ -96,6 +96,8 @@ struct SetState {
     int dense_bits = -1;           // key bits the dense table is laid out (and zeroed) for; -1 = not valid
     int dense_cells = 0;           // cells of the previous run whose entries are still set
     bool use_dense = false;
+    DevBuf first;                  // row-key mode: prefix cell table first[key] for every key in [0, 2^key_bits] (+ scan scratch behind it)
+    bool use_table = false;
     int hash_log2 = 1;
     int n_cells = 0;
     bool sorted_valid = false;     // "are_cells_valid" of the reference (TreeNSearch.cpp:148)
@@ -154,6 +156,7 @@ struct tnsb_context {
     double cell = 0.0;
     int bits = 0;
     bool key64 = false;
+    bool grid_row_mode = false;    // key order of the grid built last: row keys (round kernel) or 3-D Morton keys (cell kernel, zsort)
 
     DevBuf d_reduce;        // 8 x uint32
     DevBuf d_counters;      // PairCounters per pair
@@ -231,7 +234,7 @@ int validate(tnsb_context* c)
 }
 
 template <typename Key>
-int build_sets(tnsb_context* c, const GridParams& gp)
+int build_sets(tnsb_context* c, const GridParams& gp, bool row_mode)
 {
     cudaStream_t s = c->stream;
     int& launches = c->stats.n_kernel_launches;
@@ -243,7 +246,7 @@ int build_sets(tnsb_context* c, const GridParams& gp)
             TNSB_CUDA(c, st.keys[b].ensure(sizeof(Key) * (size_t)st.n, 1.1));
             TNSB_CUDA(c, st.vals[b].ensure(sizeof(uint32_t) * (size_t)st.n, 1.1));
         }
-        keygen_kernel<Key><<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.n, st.d_stride, gp, st.keys[0].as<Key>());
+        keygen_kernel<Key><<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.n, st.d_stride, gp, st.keys[0].as<Key>(), row_mode ? 1 : 0);
         launches++;
     }
     TNSB_CUDA(c, cudaEventRecord(c->ev[EV_KEYS], s));
@@ -288,10 +291,18 @@ int build_sets(tnsb_context* c, const GridParams& gp)
         auto& st = c->sets[si];
         st.n_cells = st.n > 0 ? (int)h_ncells[si] : 0;
         c->stats.n_cells += st.n_cells;
-        // neighbour lookup structure: a dense Morton-indexed table while the grid has <= 2^27 cells (8 bytes per cell, no probing,
-        // Morton neighbours share sectors), else an open addressing hash at <= 33% load (16-byte slots {key, start, end}).
-        st.use_dense = key_bits <= 27;
-        if (st.use_dense) {
+        // neighbour lookup structure.
+        //   row keys (round kernel): prefix table first[key] over ALL cells while that is affordable, else a hash of the occupied cells;
+        //   Morton keys (cell kernel): dense Morton-indexed {start, end} table while the grid has <= 2^27 cells, else the hash
+        //   (open addressing at <= 33% load, 16-byte slots {key, start, end}).
+        const int64_t n_keys = key_bits <= 40 ? (1ll << key_bits) : -1;
+        st.use_table = row_mode && key_bits <= 26 && n_keys <= std::max<int64_t>(1ll << 22, 8ll * st.n);
+        st.use_dense = !row_mode && key_bits <= 27;
+        if (st.use_table) {
+            const int64_t n_entries = n_keys + 1;
+            TNSB_CUDA(c, st.first.ensure(sizeof(uint32_t) * (size_t)(n_entries + exclusive_scan_temp_elems(n_entries))));
+            TNSB_CUDA(c, cudaMemsetAsync(st.first.p, 0, sizeof(uint32_t) * (size_t)n_entries, s));
+        } else if (st.use_dense) {
             const size_t dbytes = sizeof(uint2) << key_bits;
             const bool fresh = st.dense.cap < dbytes || st.dense_bits != key_bits;
             TNSB_CUDA(c, st.dense.ensure(dbytes));
@@ -306,7 +317,6 @@ int build_sets(tnsb_context* c, const GridParams& gp)
             st.dense_bits = key_bits;
             st.dense_cells = 0;
         } else {
-            st.dense_bits = -1;
             int lg = 1;
             while ((1ll << lg) < 3ll * st.n_cells) lg++;
             st.hash_log2 = lg;
@@ -314,13 +324,20 @@ int build_sets(tnsb_context* c, const GridParams& gp)
             TNSB_CUDA(c, st.htable.ensure(hbytes, 1.25));
             TNSB_CUDA(c, cudaMemsetAsync(st.htable.p, 0xff, hbytes, s));
         }
+        if (!st.use_dense) st.dense_bits = -1;
         if (st.n == 0) continue;
         TNSB_CUDA(c, st.cell_key.ensure(sizeof(Key) * ((size_t)st.n_cells + 1), 1.25));
         TNSB_CUDA(c, st.cell_start.ensure(sizeof(uint32_t) * ((size_t)st.n_cells + 2), 1.25));
         const int n_tiles = ceil_div(st.n, kCellTile);
         emit_cells_kernel<Key><<<n_tiles, kCellThreads, 0, s>>>(st.keys[st.sel].as<Key>(), st.n, st.tile_heads.as<uint32_t>(), st.cell_key.as<Key>(),
                                                               st.cell_start.as<uint32_t>());
-        if (st.use_dense) {
+        launches += 2;                   // emit_cells + the table / hash kernel below
+        if (st.use_table) {
+            const int64_t n_entries = n_keys + 1;
+            uint32_t* first = st.first.as<uint32_t>();
+            cell_population_kernel<Key><<<ceil_div(st.n_cells, 256), 256, 0, s>>>(st.cell_key.as<Key>(), st.cell_start.as<uint32_t>(), st.n_cells, first);
+            launches += exclusive_scan_u32(first, first, n_entries, first + n_entries, nullptr, s);
+        } else if (st.use_dense) {
             dense_table_kernel<Key><<<ceil_div(st.n_cells, 256), 256, 0, s>>>(st.cell_key.as<Key>(), st.cell_start.as<uint32_t>(), st.n_cells,
                                                                              st.dense.as<uint2>(), 1);
             st.dense_cells = st.n_cells;
@@ -328,7 +345,6 @@ int build_sets(tnsb_context* c, const GridParams& gp)
             build_hash_kernel<Key><<<ceil_div(st.n_cells, 256), 256, 0, s>>>(st.cell_key.as<Key>(), st.cell_start.as<uint32_t>(), st.n_cells,
                                                                             st.htable.as<typename HashSlot<Key>::Raw>(), st.hash_log2);
         }
-        launches += 2;
         st.sorted_valid = true;
     }
     TNSB_CUDA(c, cudaEventRecord(c->ev[EV_CELLS], s));
@@ -385,6 +401,8 @@ int query_pair(tnsb_context* c, int si, int sj, const GridParams& gp, PairCounte
     a.c_r2 = cj.sorted_r2.as<float>();
     a.htable = cj.htable.as<typename HashSlot<Key>::Raw>();
     a.dense = cj.dense.as<uint2>();
+    a.first = cj.first.as<uint32_t>();
+    a.bits = gp.bits;
     a.hash_log2 = cj.hash_log2;
     a.same_set = si == sj;
     a.key_mask = (Key)(((Key)1 << (3 * gp.bits)) - 1);
@@ -403,9 +421,9 @@ int query_pair(tnsb_context* c, int si, int sj, const GridParams& gp, PairCounte
     const int grid = c->n_sms;
     cudaError_t e;
     const bool small = 27.0 * avg_cell * 1.15 <= 256.0;
-    if (c->opt_query_kernel == 1) {
+    if (c->grid_row_mode) {
         // tiles of 256 candidates (4 cells per round) for the usual SPH densities, 512 (2 cells per round) for dense clouds
-        if (cj.use_dense) e = small ? launch_query_rounds<Key, 4, true>(a, variable, symmetric, grid, c->stream) : launch_query_rounds<Key, 2, true>(a, variable, symmetric, grid, c->stream);
+        if (cj.use_table) e = small ? launch_query_rounds<Key, 4, true>(a, variable, symmetric, grid, c->stream) : launch_query_rounds<Key, 2, true>(a, variable, symmetric, grid, c->stream);
         else e = small ? launch_query_rounds<Key, 4, false>(a, variable, symmetric, grid, c->stream) : launch_query_rounds<Key, 2, false>(a, variable, symmetric, grid, c->stream);
     } else if (cj.use_dense) e = small ? launch_query<Key, 8, true>(a, variable, symmetric, grid, c->stream) : launch_query<Key, 16, true>(a, variable, symmetric, grid, c->stream);
     else e = small ? launch_query<Key, 8, false>(a, variable, symmetric, grid, c->stream) : launch_query<Key, 16, false>(a, variable, symmetric, grid, c->stream);
@@ -421,7 +439,7 @@ double ms_since(const std::chrono::steady_clock::time_point& t0)
 }
 
 // upload + world box + grid parameters + sorted grid of every set.  Shared by run() and prepare_zsort().
-int build_grid(tnsb_context* c, GridParams* gp_out)
+int build_grid(tnsb_context* c, GridParams* gp_out, bool row_mode)
 {
     cudaStream_t s = c->stream;
     const int n_sets = (int)c->sets.size();
@@ -519,7 +537,8 @@ int build_grid(tnsb_context* c, GridParams* gp_out)
     c->stats.key_bits = 3 * c->bits;
     for (int d = 0; d < 3; d++) { c->stats.domain_bottom[d] = (float)c->dom_bottom[d]; c->stats.domain_top[d] = (float)c->dom_top[d]; }
 
-    return c->key64 ? build_sets<uint64_t>(c, gp) : build_sets<uint32_t>(c, gp);
+    c->grid_row_mode = row_mode;
+    return c->key64 ? build_sets<uint64_t>(c, gp, row_mode) : build_sets<uint32_t>(c, gp, row_mode);
 }
 
 float ev_ms(tnsb_context* c, int a, int b)
@@ -548,7 +567,7 @@ int run_impl(tnsb_context* c)
     GridParams gp;
     memset(&gp, 0, sizeof(gp));
     if (n_total > 0) {
-        rc = build_grid(c, &gp);
+        rc = build_grid(c, &gp, c->opt_query_kernel == 1);
         if (rc != TNSB_OK) return rc;
     } else {
         for (int k = 0; k < EV_COUNT; k++) TNSB_CUDA(c, cudaEventRecord(c->ev[k], s));
@@ -747,7 +766,7 @@ void tnsb_destroy(tnsb_context* c)
         st.up_pts.release(); st.up_radii.release(); st.cv_pts.release(); st.cv_radii.release();
         for (int b = 0; b < 2; b++) { st.keys[b].release(); st.vals[b].release(); }
         st.sorted.release(); st.sorted_r2.release(); st.cell_key.release(); st.cell_start.release(); st.tile_heads.release();
-        st.htable.release(); st.dense.release(); st.d_zorder.release();
+        st.htable.release(); st.dense.release(); st.first.release(); st.d_zorder.release();
     }
     for (auto& p : c->pairs) { p.d_ragged.release(); p.d_list_pos.release(); p.h_ragged.release(); p.h_list_pos.release(); }
     c->d_reduce.release(); c->d_counters.release(); c->d_misc.release(); c->sort_temp.release(); c->scan_temp.release(); c->h_small.release();
@@ -972,11 +991,12 @@ int tnsb_prepare_zsort(tnsb_context* c)
     bool all_valid = true;
     int64_t n_total = 0;
     for (auto& st : c->sets) { all_valid = all_valid && (st.sorted_valid || st.n == 0); n_total += st.n; }
-    if (!all_valid && n_total > 0) {
-        // no grid of the current points yet (TreeNSearch.cpp:2592-2595): build it now
+    if ((!all_valid || c->grid_row_mode) && n_total > 0) {
+        // no grid of the current points yet (TreeNSearch.cpp:2592-2595), or a grid in row-key order: the order handed to the user
+        // is the libmorton Z-order, so sort by 3-D Morton keys now
         GridParams gp;
         memset(&c->stats, 0, sizeof(c->stats));
-        rc = build_grid(c, &gp);
+        rc = build_grid(c, &gp, false);
         if (rc != TNSB_OK) return rc;
     }
     for (auto& st : c->sets) {
