@@ -51,9 +51,17 @@ enum {
                                     memory (PCIe writes overlap the search, no HBM copy of the ids, no D2H afterwards; measured 28.1 ms
                                     vs 29.7 ms end to end at 10M points); 0 = lists in HBM, then one D2H copy.  Ignored (HBM path) when
                                     TNSB_OPT_SORT_LISTS is set or HOST_RESULTS is 0 */
-    TNSB_OPT_QUERY_KERNEL = 8,   /* which 27-cell query kernel runs: 1 (default) = query_rounds_kernel (a lane owns a QUERY, candidate tiles in
-                                    shared memory, private hit lists), 0 = query_kernel (a lane owns a CANDIDATE, ballot compaction).
-                                    Same results; the environment variable TNSB_QUERY_KERNEL=0|1 sets the default of new contexts */
+    TNSB_OPT_QUERY_KERNEL = 8,   /* which 27-cell query kernel runs: 0 (default) = query_kernel (grid sorted by 3-D Morton keys, a lane owns a
+                                    CANDIDATE, ballot compaction), 1 = query_rounds_kernel (grid sorted by row keys + prefix cell table, a lane
+                                    owns a QUERY, candidate tiles in shared memory, private hit lists).  Same neighbour sets; measured on B200
+                                    (DESIGN.md §4): kernel 0 is faster at 10M points (2.57 vs 2.98 ms uniform, 3.59 vs 5.01 ms dam-break).
+                                    The environment variable TNSB_QUERY_KERNEL=0|1 sets the default of new contexts */
+    TNSB_OPT_BUILD = 9,          /* how the sorted grid is built: 0 (default) = automatic: a bucket build (ONE counting pass over the full cell
+                                    key: cell populations by L2 atomics, exclusive scan, scatter of the (x, y, z, id) records) while the cell
+                                    table is small next to the point count, else the LSD radix sort of (key, index) pairs; 1 = always the
+                                    radix sort (stable: points of a cell keep their input order; the bucket build leaves them in arrival
+                                    order, which changes the order INSIDE neighbour lists, never the sets).  TNSB_BUILD=0|1 in the
+                                    environment sets the default of new contexts */
     TNSB_OPT_POINT_STRIDE = 6    /* floats between consecutive points of float32 sets: 3 (default, xyzxyz as in the reference) or
                                     4 ((x, y, z, id) records as produced by tnsb_shard_partition; the 4th word is ignored) */
 };

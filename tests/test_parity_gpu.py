@@ -407,3 +407,75 @@ def test_set_active_search_overloads(tnsb):
     eng.set_all_searches(True)
     assert all(eng.is_search_active(i, j) for i in range(3) for j in range(3))
     assert eng.does_set_exist(2) and not eng.does_set_exist(3)
+
+
+# ---------------------------------------------------------------------------------------------------- the round kernel (option 1)
+# TNSB_OPT_QUERY_KERNEL = 1: grid sorted by row keys + prefix cell table, a lane owns a query (csrc/query_rounds.cuh).  Same contract.
+@pytest.mark.parametrize("name", list(cases.GOLDEN_CASES))
+def test_round_kernel_golden(tnsb, golden, name):
+    case = cases.GOLDEN_CASES[name]()
+    eng = run_engine(tnsb, case, options={tnsb.TNSB_OPT_QUERY_KERNEL: 1})
+    for (i, j) in case["pairs"]:
+        off, idx = eng.neighbor_csr(i, j)
+        assert np.array_equal(off, golden[f"{name}/{i}_{j}/offsets"]), (name, i, j)
+        assert np.array_equal(idx, golden[f"{name}/{i}_{j}/indices"]), (name, i, j)
+
+
+def test_round_kernel_slow_paths_and_limits(tnsb):
+    opt = {tnsb.TNSB_OPT_QUERY_KERNEL: 1}
+    # neighbourhoods larger than a tile, lists longer than the private lists and than the staging buffer
+    rs = np.random.RandomState(8)
+    blob = (0.5 + 0.002 * rs.standard_normal((2600, 3))).astype(np.float32)
+    bg = rs.random_sample((3000, 3)).astype(np.float32)
+    pts = np.ascontiguousarray(np.concatenate([blob, bg]))
+    case = dict(sets=[(pts, None)], radius=0.04, pairs=[(0, 0)], symmetric=True)
+    eng = run_engine(tnsb, case, options=opt)
+    assert eng.stats()["n_neighbors"] > 2600 * 2500
+    assert_matches_port(eng, case)
+    # 64-bit keys on a sparse domain: hash of the occupied cells instead of the prefix table
+    rs = np.random.RandomState(3)
+    centers = rs.random_sample((40, 3)) * 1000.0
+    pts = np.ascontiguousarray((centers[rs.randint(0, 40, 4000)] + 0.05 * rs.standard_normal((4000, 3))).astype(np.float32))
+    case = dict(sets=[(pts, None)], radius=0.02, pairs=[(0, 0)], symmetric=True)
+    eng = run_engine(tnsb, case, options=opt)
+    assert eng.stats()["key_bits"] > 32
+    assert_matches_port(eng, case)
+    # halo points (find-only) + list buffer overflow re-run
+    case = cases.GOLDEN_CASES["uniform_fixed_5000"]()
+    eng = run_engine(tnsb, case, options={tnsb.TNSB_OPT_QUERY_KERNEL: 1, tnsb.TNSB_OPT_LIST_CAPACITY: 1})
+    assert eng.stats()["n_reruns"] >= 1
+    assert_matches_port(eng, case)
+
+
+def test_round_kernel_c1_and_zsort(tnsb):
+    n = 100_000
+    pts = clouds.uniform_cloud(n, 42).copy()
+    r = float(clouds.radius_for_mean_neighbors(n))
+    case = dict(sets=[(pts, None)], radius=r, pairs=[(0, 0)], symmetric=True)
+    eng = run_engine(tnsb, case, options={tnsb.TNSB_OPT_QUERY_KERNEL: 1})
+    assert_matches_port(eng, case)
+    # the order handed to the user is still the libmorton Z-order, although the grid itself is sorted by row keys
+    eng.prepare_zsort()
+    order = eng.get_zsort_order(0).copy()
+    assert np.array_equal(np.sort(order), np.arange(n))
+    eng.apply_zsort(0, pts, 3)
+    eng.run()
+    st = eng.stats()
+    cell = np.floor((pts.astype(np.float64) - np.array(st["domain_bottom"], np.float64)) / (r * (1.0 + 1.0 / 8192.0))).astype(np.int64)
+    keys = np.array([loader.morton3d_64(*c) for c in cell[::211]], dtype=np.uint64)
+    assert np.all(np.diff(keys.astype(np.int64)) >= 0)
+    assert_matches_port(eng, dict(sets=[(pts, None)], radius=r, pairs=[(0, 0)], symmetric=True))
+
+
+# ---------------------------------------------------------------------------------------------------- build paths
+@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("name", ["uniform_fixed_5000", "variable_random_sym", "clustered_blob", "duplicates", "three_sets_all_pairs"])
+def test_radix_build_matches_golden(tnsb, golden, name, kernel):
+    """TNSB_OPT_BUILD = 1 forces the LSD radix sort (the default picks the bucket build for these small dense grids)."""
+    case = cases.GOLDEN_CASES[name]()
+    eng = run_engine(tnsb, case, options={tnsb.TNSB_OPT_BUILD: 1, tnsb.TNSB_OPT_QUERY_KERNEL: kernel})
+    assert eng.stats()["sort_passes"] >= 1
+    for (i, j) in case["pairs"]:
+        off, idx = eng.neighbor_csr(i, j)
+        assert np.array_equal(off, golden[f"{name}/{i}_{j}/offsets"]), (name, i, j)
+        assert np.array_equal(idx, golden[f"{name}/{i}_{j}/indices"]), (name, i, j)

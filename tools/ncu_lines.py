@@ -42,3 +42,20 @@ print(f"total executed warp instructions {tot:.4g}, samples {tots:.0f}")
 print("file:line              ex%    smp%   smem wavefronts (ideal)   source")
 for (f, ln), a in sorted(agg.items(), key=lambda kv: -kv[1][key])[:top]:
     print(f"{f + ':' + ln:22s} {100 * a[0] / tot:5.2f}  {100 * a[1] / tots:5.2f}  {a[2]:12.4g} ({a[3]:10.4g})  {a[4]}")
+
+# optional: sums over line ranges of one file:  ncu_lines.py rep N key file:lo-hi[:name] ...
+if len(sys.argv) > 4:
+    print("-- ranges")
+    for spec in sys.argv[4:]:
+        parts = spec.split(":")
+        f, rng = parts[0], parts[1]
+        name = parts[2] if len(parts) > 2 else rng
+        lo, hi = (int(x) for x in rng.split("-"))
+        ex = sum(a[0] for (ff, ln), a in agg.items() if ff == f and lo <= int(ln) <= hi)
+        sm = sum(a[1] for (ff, ln), a in agg.items() if ff == f and lo <= int(ln) <= hi)
+        print(f"  {name:28s} ex {100 * ex / tot:5.2f}%  smp {100 * sm / tots:5.2f}%")
+    others = defaultdict(lambda: [0.0, 0.0])
+    for (ff, ln), a in agg.items():
+        others[ff][0] += a[0]; others[ff][1] += a[1]
+    for ff, a in sorted(others.items(), key=lambda kv: -kv[1][0]):
+        print(f"  file {ff:30s} ex {100 * a[0] / tot:5.2f}%  smp {100 * a[1] / tots:5.2f}%")

@@ -7,6 +7,6 @@ Python host-side mirror of the reference's public class; the C++ mirror is inclu
 from .api import NeighborList, TreeNSearch, TreeNSearchError  # noqa: F401
 from . import clouds  # noqa: F401
 from ._lib import (TNSB_OPT_HOST_RESULTS, TNSB_OPT_LIST_CAPACITY, TNSB_OPT_PIN_USER_MEMORY,  # noqa: F401
-                   TNSB_OPT_QUERY_LIMIT, TNSB_OPT_SORT_LISTS, TNSB_OPT_POINT_STRIDE, TNSB_OPT_ZERO_COPY_RESULTS, TNSB_OPT_QUERY_KERNEL, LIB_PATH)
+                   TNSB_OPT_QUERY_LIMIT, TNSB_OPT_SORT_LISTS, TNSB_OPT_POINT_STRIDE, TNSB_OPT_ZERO_COPY_RESULTS, TNSB_OPT_QUERY_KERNEL, TNSB_OPT_BUILD, LIB_PATH)
 
 __all__ = ["TreeNSearch", "NeighborList", "TreeNSearchError", "clouds"]

@@ -26,6 +26,7 @@ TNSB_OPT_SORT_LISTS = 5
 TNSB_OPT_POINT_STRIDE = 6
 TNSB_OPT_ZERO_COPY_RESULTS = 7
 TNSB_OPT_QUERY_KERNEL = 8
+TNSB_OPT_BUILD = 9
 
 
 class Stats(C.Structure):

@@ -198,6 +198,100 @@ __global__ void __launch_bounds__(256) dense_table_kernel(const Key* __restrict_
     table[cell_key[c]] = fill ? make_uint2(cell_start[c], cell_start[c + 1]) : make_uint2(0u, 0u);
 }
 
+// ----------------------------------------------------------------------------------------------------------------------
+// Bucket build: when the cell table (one counter per cell of the whole grid) is small next to the point count, the sort of
+// (cell key, index) pairs collapses into ONE counting pass over the full key -- histogram, exclusive scan, scatter -- instead
+// of ceil(key_bits / 8) LSD radix passes, and the scatter writes the reordered float4 records directly (no separate gather).
+//   keygen_count_kernel   key of every point + its rank inside its cell = old value of the cell's population counter (ONE L2 atomic
+//                         per point on an L2 resident table)
+//   exclusive_scan_u32    first[k] = number of points with a smaller key, for every k in [0, 2^key_bits]
+//   bucket_scatter_kernel sorted[first[key] + rank] = (x, y, z, bits(index)): a plain scatter, no second round of atomics
+//   table_count/emit      compact list of the occupied cells (the query's task list) + the cell kernel's {start, end} table
+// The order of the points INSIDE a cell is the arrival order of the atomics (not the input order as with the stable radix
+// sort); neighbour SETS do not depend on it.  prepare_zsort() and TNSB_OPT_BUILD = 1 use the radix path.
+template <typename Key>
+__global__ void __launch_bounds__(256) keygen_count_kernel(const float* __restrict__ pts, int n, int stride, GridParams g, Key* __restrict__ keys, int row_order,
+                                                           uint32_t* __restrict__ population, uint32_t* __restrict__ rank)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = pts + (int64_t)i * stride;
+    const float x = p[0], y = p[1], z = p[2];
+    int cx = __double2int_rd(((double)x - g.bottom[0]) * g.inv_cell);
+    int cy = __double2int_rd(((double)y - g.bottom[1]) * g.inv_cell);
+    int cz = __double2int_rd(((double)z - g.bottom[2]) * g.inv_cell);
+    cx = min(max(cx, 0), g.max_coord);
+    cy = min(max(cy, 0), g.max_coord);
+    cz = min(max(cz, 0), g.max_coord);
+    const Key k = row_order ? RowKey<Key>::encode((uint32_t)cx, (uint32_t)cy, (uint32_t)cz, g.bits) : Morton<Key>::encode((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+    keys[i] = k;
+    rank[i] = atomicAdd(population + k, 1u);
+}
+
+template <typename Key>
+__global__ void __launch_bounds__(256) bucket_scatter_kernel(const float* __restrict__ pts, int stride, const float* __restrict__ radii, const Key* __restrict__ keys,
+                                                             int n, const uint32_t* __restrict__ first, const uint32_t* __restrict__ rank, float4* __restrict__ sorted,
+                                                             float* __restrict__ sorted_r2)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = pts + (int64_t)i * stride;
+    const float x = p[0], y = p[1], z = p[2];
+    const uint32_t pos = first[keys[i]] + rank[i];
+    sorted[pos] = make_float4(x, y, z, __uint_as_float((uint32_t)i));
+    if (radii) {
+        const float r = radii[i];
+        sorted_r2[pos] = __fmul_rn(r, r);
+    }
+}
+
+// occupied cells of the prefix table first[0 .. n_keys]: count per tile, then (after a scan of the tile counts) emit
+// cell_key / cell_start in key order; optionally fills the cell kernel's dense {start, end} table for every key
+__global__ void __launch_bounds__(kCellThreads) table_count_kernel(const uint32_t* __restrict__ first, int64_t n_keys, uint32_t* __restrict__ tile_cells)
+{
+    __shared__ uint32_t warp_sums[8];
+    const int64_t base = (int64_t)blockIdx.x * kCellTile + (int64_t)threadIdx.x * kCellItems;
+    uint32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < kCellItems; i++) {
+        const int64_t k = base + i;
+        if (k < n_keys) c += first[k + 1] > first[k] ? 1u : 0u;
+    }
+    uint32_t total;
+    block_exclusive_scan_256(c, warp_sums, total);
+    if (threadIdx.x == 0) tile_cells[blockIdx.x] = total;
+}
+
+template <typename Key>
+__global__ void __launch_bounds__(kCellThreads) table_emit_kernel(const uint32_t* __restrict__ first, int64_t n_keys, const uint32_t* __restrict__ tile_base,
+                                                                  Key* __restrict__ cell_key, uint32_t* __restrict__ cell_start, uint2* __restrict__ dense)
+{
+    __shared__ uint32_t warp_sums[8];
+    const int64_t base = (int64_t)blockIdx.x * kCellTile + (int64_t)threadIdx.x * kCellItems;
+    uint32_t lo[kCellItems + 1];
+#pragma unroll
+    for (int i = 0; i <= kCellItems; i++) lo[i] = (base + i <= n_keys) ? first[base + i] : 0u;
+    uint32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < kCellItems; i++)
+        if (base + i < n_keys) {
+            c += lo[i + 1] > lo[i] ? 1u : 0u;
+            if (dense) dense[base + i] = make_uint2(lo[i], lo[i + 1]);
+        }
+    uint32_t total;
+    uint32_t cid = block_exclusive_scan_256(c, warp_sums, total) + tile_base[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < kCellItems; i++) {
+        if (base + i < n_keys && lo[i + 1] > lo[i]) {
+            cell_key[cid] = (Key)(base + i);
+            cell_start[cid] = lo[i];
+            cid++;
+        }
+    }
+    // sentinel: cell_start[n_cells] = n (= first[n_keys])
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kCellThreads - 1) cell_start[cid] = first[n_keys];
+}
+
 // prefix cell table, step 1: population of every occupied cell at table[key] (the table was zeroed); an exclusive scan then turns
 // it into first[key] = number of points with a smaller key, valid for EVERY key in [0, 2^key_bits] (empty cells included)
 template <typename Key>

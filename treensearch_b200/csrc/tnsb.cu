@@ -96,8 +96,10 @@ struct SetState {
     int dense_bits = -1;           // key bits the dense table is laid out (and zeroed) for; -1 = not valid
     int dense_cells = 0;           // cells of the previous run whose entries are still set
     bool use_dense = false;
-    DevBuf first;                  // row-key mode: prefix cell table first[key] for every key in [0, 2^key_bits] (+ scan scratch behind it)
+    DevBuf first;                  // prefix cell table first[key] for every key in [0, 2^key_bits] (+ scan scratch behind it): bucket build, row-key mode
     bool use_table = false;
+    bool bucket = false;           // the last build of this set was a bucket build (no sorted permutation in vals[])
+    bool order_valid = false;      // vals[sel] holds the stable sorted permutation of the last build
     int hash_log2 = 1;
     int n_cells = 0;
     bool sorted_valid = false;     // "are_cells_valid" of the reference (TreeNSearch.cpp:148)
@@ -148,7 +150,8 @@ struct tnsb_context {
     bool opt_sort_lists = false;
     bool opt_zero_copy = true;
     int opt_point_stride = 3;
-    int opt_query_kernel = 1;      // 0: query_kernel (candidates in registers, lane = candidate), 1: query_rounds_kernel (lane = query)
+    int opt_build = 0;             // 0: bucket build when the cell table is small enough, else radix sort; 1: always radix sort
+    int opt_query_kernel = 0;      // 0: query_kernel (candidates in registers, lane = candidate; Morton keys), 1: query_rounds_kernel (lane = query; row keys)
 
     // world box with hysteresis (TreeNSearch.cpp:474-482)
     bool domain_valid = false;
@@ -234,54 +237,84 @@ int validate(tnsb_context* c)
 }
 
 template <typename Key>
-int build_sets(tnsb_context* c, const GridParams& gp, bool row_mode)
+int build_sets(tnsb_context* c, const GridParams& gp, bool row_mode, bool need_order)
 {
     cudaStream_t s = c->stream;
     int& launches = c->stats.n_kernel_launches;
     const int key_bits = 3 * gp.bits;
-    // ---- cell assignment + Morton keys
+    const int n_sets = (int)c->sets.size();
+    const int64_t n_keys = key_bits <= 40 ? (1ll << key_bits) : -1;
+    // Per set: bucket build (one counting pass over the full cell key, see grid_build.cuh) while the cell table is small next to the
+    // point count, else -- huge sparse domains, 64-bit keys, prepare_zsort (needs the stable permutation), TNSB_OPT_BUILD = 1 -- the LSD
+    // radix sort of (key, index) pairs.
+    for (auto& st : c->sets) {
+        st.bucket = !need_order && c->opt_build == 0 && st.n > 0 && sizeof(Key) == 4 && key_bits <= 26 && n_keys <= std::max<int64_t>(1ll << 22, 4ll * st.n);
+        st.order_valid = false;
+    }
+    // ---- cell assignment + keys (+ cell populations)
     for (auto& st : c->sets) {
         if (st.n == 0) continue;
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < (st.bucket ? 1 : 2); b++) {
             TNSB_CUDA(c, st.keys[b].ensure(sizeof(Key) * (size_t)st.n, 1.1));
-            TNSB_CUDA(c, st.vals[b].ensure(sizeof(uint32_t) * (size_t)st.n, 1.1));
+            TNSB_CUDA(c, st.vals[b].ensure(sizeof(uint32_t) * (size_t)st.n, 1.1));       // bucket build: vals[0] = rank of the point inside its cell
         }
-        keygen_kernel<Key><<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.n, st.d_stride, gp, st.keys[0].as<Key>(), row_mode ? 1 : 0);
+        if (st.bucket) {
+            const int64_t n_entries = n_keys + 1;
+            TNSB_CUDA(c, st.first.ensure(sizeof(uint32_t) * (size_t)(n_entries + exclusive_scan_temp_elems(n_entries))));
+            TNSB_CUDA(c, cudaMemsetAsync(st.first.p, 0, sizeof(uint32_t) * (size_t)n_entries, s));
+            keygen_count_kernel<Key><<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.n, st.d_stride, gp, st.keys[0].as<Key>(), row_mode ? 1 : 0, st.first.as<uint32_t>(),
+                                                                        st.vals[0].as<uint32_t>());
+        } else {
+            keygen_kernel<Key><<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.n, st.d_stride, gp, st.keys[0].as<Key>(), row_mode ? 1 : 0);
+        }
         launches++;
     }
     TNSB_CUDA(c, cudaEventRecord(c->ev[EV_KEYS], s));
-    // ---- radix sort of (key, index)
+    // ---- sort: exclusive scan of the cell populations (bucket) / radix sort of (key, index)
     for (auto& st : c->sets) {
         if (st.n == 0) continue;
-        TNSB_CUDA(c, c->sort_temp.ensure(sizeof(uint32_t) * (size_t)radix_sort_temp_elems<Key>(st.n), 1.1));
-        Key* keys[2] = { st.keys[0].as<Key>(), st.keys[1].as<Key>() };
-        uint32_t* vals[2] = { st.vals[0].as<uint32_t>(), st.vals[1].as<uint32_t>() };
-        int passes = 0;
-        st.sel = radix_sort_pairs<Key>(keys, vals, st.n, key_bits, c->sort_temp.as<uint32_t>(), s, &launches, &passes);
-        c->stats.sort_passes = std::max(c->stats.sort_passes, passes);
+        if (st.bucket) {
+            const int64_t n_entries = n_keys + 1;
+            uint32_t* first = st.first.as<uint32_t>();
+            launches += exclusive_scan_u32(first, first, n_entries, first + n_entries, nullptr, s);
+            c->stats.sort_passes = std::max(c->stats.sort_passes, 1);
+        } else {
+            TNSB_CUDA(c, c->sort_temp.ensure(sizeof(uint32_t) * (size_t)radix_sort_temp_elems<Key>(st.n), 1.1));
+            Key* keys[2] = { st.keys[0].as<Key>(), st.keys[1].as<Key>() };
+            uint32_t* vals[2] = { st.vals[0].as<uint32_t>(), st.vals[1].as<uint32_t>() };
+            int passes = 0;
+            st.sel = radix_sort_pairs<Key>(keys, vals, st.n, key_bits, c->sort_temp.as<uint32_t>(), s, &launches, &passes);
+            c->stats.sort_passes = std::max(c->stats.sort_passes, passes);
+            st.order_valid = true;
+        }
     }
     TNSB_CUDA(c, cudaEventRecord(c->ev[EV_SORT], s));
-    // ---- reorder
+    // ---- reorder: scatter into the cells (bucket) / gather through the sorted permutation (radix)
     for (auto& st : c->sets) {
         if (st.n == 0) continue;
         TNSB_CUDA(c, st.sorted.ensure(sizeof(float4) * (size_t)st.n, 1.1));
         if (st.has_radii) TNSB_CUDA(c, st.sorted_r2.ensure(sizeof(float) * (size_t)st.n, 1.1));
-        reorder_kernel<<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.d_stride, st.has_radii ? st.d_radii : nullptr, st.vals[st.sel].as<uint32_t>(), st.n,
-                                                          st.sorted.as<float4>(), st.sorted_r2.as<float>());
+        if (st.bucket)
+            bucket_scatter_kernel<Key><<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.d_stride, st.has_radii ? st.d_radii : nullptr, st.keys[0].as<Key>(), st.n,
+                                                                          st.first.as<uint32_t>(), st.vals[0].as<uint32_t>(), st.sorted.as<float4>(),
+                                                                          st.sorted_r2.as<float>());
+        else
+            reorder_kernel<<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.d_stride, st.has_radii ? st.d_radii : nullptr, st.vals[st.sel].as<uint32_t>(), st.n,
+                                                              st.sorted.as<float4>(), st.sorted_r2.as<float>());
         launches++;
     }
     TNSB_CUDA(c, cudaEventRecord(c->ev[EV_REORDER], s));
-    // ---- cell heads: count, scan, (one sync for the cell counts), emit + hash
-    const int n_sets = (int)c->sets.size();
+    // ---- occupied cells: count, scan, (one sync for the cell counts), emit + lookup structure
     TNSB_CUDA(c, c->d_misc.ensure(sizeof(uint32_t) * (size_t)std::max(n_sets, 1)));
     for (int si = 0; si < n_sets; si++) {
         auto& st = c->sets[si];
         st.n_cells = 0;
         if (st.n == 0) continue;
-        const int n_tiles = ceil_div(st.n, kCellTile);
+        const int n_tiles = st.bucket ? (int)ceil_div64(n_keys, kCellTile) : ceil_div(st.n, kCellTile);
         TNSB_CUDA(c, st.tile_heads.ensure(sizeof(uint32_t) * ((size_t)n_tiles + exclusive_scan_temp_elems(n_tiles)), 1.1));
         uint32_t* th = st.tile_heads.as<uint32_t>();
-        count_heads_kernel<Key><<<n_tiles, kCellThreads, 0, s>>>(st.keys[st.sel].as<Key>(), st.n, th);
+        if (st.bucket) table_count_kernel<<<n_tiles, kCellThreads, 0, s>>>(st.first.as<uint32_t>(), n_keys, th);
+        else count_heads_kernel<Key><<<n_tiles, kCellThreads, 0, s>>>(st.keys[st.sel].as<Key>(), st.n, th);
         launches += 1 + exclusive_scan_u32(th, th, n_tiles, th + n_tiles, c->d_misc.as<uint32_t>() + si, s);
     }
     uint32_t* h_ncells = c->h_small.as<uint32_t>() + 64;
@@ -295,10 +328,9 @@ int build_sets(tnsb_context* c, const GridParams& gp, bool row_mode)
         //   row keys (round kernel): prefix table first[key] over ALL cells while that is affordable, else a hash of the occupied cells;
         //   Morton keys (cell kernel): dense Morton-indexed {start, end} table while the grid has <= 2^27 cells, else the hash
         //   (open addressing at <= 33% load, 16-byte slots {key, start, end}).
-        const int64_t n_keys = key_bits <= 40 ? (1ll << key_bits) : -1;
-        st.use_table = row_mode && key_bits <= 26 && n_keys <= std::max<int64_t>(1ll << 22, 8ll * st.n);
+        st.use_table = row_mode && (st.bucket || (key_bits <= 26 && n_keys <= std::max<int64_t>(1ll << 22, 8ll * st.n)));
         st.use_dense = !row_mode && key_bits <= 27;
-        if (st.use_table) {
+        if (st.use_table && !st.bucket) {
             const int64_t n_entries = n_keys + 1;
             TNSB_CUDA(c, st.first.ensure(sizeof(uint32_t) * (size_t)(n_entries + exclusive_scan_temp_elems(n_entries))));
             TNSB_CUDA(c, cudaMemsetAsync(st.first.p, 0, sizeof(uint32_t) * (size_t)n_entries, s));
@@ -306,7 +338,9 @@ int build_sets(tnsb_context* c, const GridParams& gp, bool row_mode)
             const size_t dbytes = sizeof(uint2) << key_bits;
             const bool fresh = st.dense.cap < dbytes || st.dense_bits != key_bits;
             TNSB_CUDA(c, st.dense.ensure(dbytes));
-            if (fresh) {
+            if (st.bucket) {
+                // table_emit_kernel below rewrites every entry
+            } else if (fresh) {
                 TNSB_CUDA(c, cudaMemsetAsync(st.dense.p, 0, dbytes, s));
             } else if (st.dense_cells > 0) {
                 // un-set only what the previous run wrote (its cell keys are still in cell_key)
@@ -316,7 +350,7 @@ int build_sets(tnsb_context* c, const GridParams& gp, bool row_mode)
             }
             st.dense_bits = key_bits;
             st.dense_cells = 0;
-        } else {
+        } else if (!st.use_table) {
             int lg = 1;
             while ((1ll << lg) < 3ll * st.n_cells) lg++;
             st.hash_log2 = lg;
@@ -328,22 +362,31 @@ int build_sets(tnsb_context* c, const GridParams& gp, bool row_mode)
         if (st.n == 0) continue;
         TNSB_CUDA(c, st.cell_key.ensure(sizeof(Key) * ((size_t)st.n_cells + 1), 1.25));
         TNSB_CUDA(c, st.cell_start.ensure(sizeof(uint32_t) * ((size_t)st.n_cells + 2), 1.25));
-        const int n_tiles = ceil_div(st.n, kCellTile);
-        emit_cells_kernel<Key><<<n_tiles, kCellThreads, 0, s>>>(st.keys[st.sel].as<Key>(), st.n, st.tile_heads.as<uint32_t>(), st.cell_key.as<Key>(),
-                                                              st.cell_start.as<uint32_t>());
-        launches += 2;                   // emit_cells + the table / hash kernel below
-        if (st.use_table) {
-            const int64_t n_entries = n_keys + 1;
-            uint32_t* first = st.first.as<uint32_t>();
-            cell_population_kernel<Key><<<ceil_div(st.n_cells, 256), 256, 0, s>>>(st.cell_key.as<Key>(), st.cell_start.as<uint32_t>(), st.n_cells, first);
-            launches += exclusive_scan_u32(first, first, n_entries, first + n_entries, nullptr, s);
-        } else if (st.use_dense) {
-            dense_table_kernel<Key><<<ceil_div(st.n_cells, 256), 256, 0, s>>>(st.cell_key.as<Key>(), st.cell_start.as<uint32_t>(), st.n_cells,
-                                                                             st.dense.as<uint2>(), 1);
-            st.dense_cells = st.n_cells;
+        if (st.bucket) {
+            const int n_tiles = (int)ceil_div64(n_keys, kCellTile);
+            table_emit_kernel<Key><<<n_tiles, kCellThreads, 0, s>>>(st.first.as<uint32_t>(), n_keys, st.tile_heads.as<uint32_t>(), st.cell_key.as<Key>(),
+                                                                  st.cell_start.as<uint32_t>(), st.use_dense ? st.dense.as<uint2>() : nullptr);
+            launches++;
+            if (st.use_dense) st.dense_cells = 0;      // every entry is rewritten by the next bucket build; a later radix build starts from a fresh table
+            if (st.use_dense) st.dense_bits = -2;
         } else {
-            build_hash_kernel<Key><<<ceil_div(st.n_cells, 256), 256, 0, s>>>(st.cell_key.as<Key>(), st.cell_start.as<uint32_t>(), st.n_cells,
-                                                                            st.htable.as<typename HashSlot<Key>::Raw>(), st.hash_log2);
+            const int n_tiles = ceil_div(st.n, kCellTile);
+            emit_cells_kernel<Key><<<n_tiles, kCellThreads, 0, s>>>(st.keys[st.sel].as<Key>(), st.n, st.tile_heads.as<uint32_t>(), st.cell_key.as<Key>(),
+                                                                  st.cell_start.as<uint32_t>());
+            launches += 2;                   // emit_cells + the table / hash kernel below
+            if (st.use_table) {
+                const int64_t n_entries = n_keys + 1;
+                uint32_t* first = st.first.as<uint32_t>();
+                cell_population_kernel<Key><<<ceil_div(st.n_cells, 256), 256, 0, s>>>(st.cell_key.as<Key>(), st.cell_start.as<uint32_t>(), st.n_cells, first);
+                launches += exclusive_scan_u32(first, first, n_entries, first + n_entries, nullptr, s);
+            } else if (st.use_dense) {
+                dense_table_kernel<Key><<<ceil_div(st.n_cells, 256), 256, 0, s>>>(st.cell_key.as<Key>(), st.cell_start.as<uint32_t>(), st.n_cells,
+                                                                                 st.dense.as<uint2>(), 1);
+                st.dense_cells = st.n_cells;
+            } else {
+                build_hash_kernel<Key><<<ceil_div(st.n_cells, 256), 256, 0, s>>>(st.cell_key.as<Key>(), st.cell_start.as<uint32_t>(), st.n_cells,
+                                                                                st.htable.as<typename HashSlot<Key>::Raw>(), st.hash_log2);
+            }
         }
         st.sorted_valid = true;
     }
@@ -439,7 +482,7 @@ double ms_since(const std::chrono::steady_clock::time_point& t0)
 }
 
 // upload + world box + grid parameters + sorted grid of every set.  Shared by run() and prepare_zsort().
-int build_grid(tnsb_context* c, GridParams* gp_out, bool row_mode)
+int build_grid(tnsb_context* c, GridParams* gp_out, bool row_mode, bool need_order)
 {
     cudaStream_t s = c->stream;
     const int n_sets = (int)c->sets.size();
@@ -538,7 +581,7 @@ int build_grid(tnsb_context* c, GridParams* gp_out, bool row_mode)
     for (int d = 0; d < 3; d++) { c->stats.domain_bottom[d] = (float)c->dom_bottom[d]; c->stats.domain_top[d] = (float)c->dom_top[d]; }
 
     c->grid_row_mode = row_mode;
-    return c->key64 ? build_sets<uint64_t>(c, gp, row_mode) : build_sets<uint32_t>(c, gp, row_mode);
+    return c->key64 ? build_sets<uint64_t>(c, gp, row_mode, need_order) : build_sets<uint32_t>(c, gp, row_mode, need_order);
 }
 
 float ev_ms(tnsb_context* c, int a, int b)
@@ -567,7 +610,7 @@ int run_impl(tnsb_context* c)
     GridParams gp;
     memset(&gp, 0, sizeof(gp));
     if (n_total > 0) {
-        rc = build_grid(c, &gp, c->opt_query_kernel == 1);
+        rc = build_grid(c, &gp, c->opt_query_kernel == 1, false);
         if (rc != TNSB_OK) return rc;
     } else {
         for (int k = 0; k < EV_COUNT; k++) TNSB_CUDA(c, cudaEventRecord(c->ev[k], s));
@@ -750,7 +793,8 @@ int tnsb_create(tnsb_context** out, int device)
         return TNSB_ERR_CUDA;
     }
     c->own_stream = c->stream;
-    if (const char* qk = getenv("TNSB_QUERY_KERNEL")) c->opt_query_kernel = (qk[0] == '0') ? 0 : 1;      // A/B switch for tests and profiling
+    if (const char* qk = getenv("TNSB_QUERY_KERNEL")) c->opt_query_kernel = (qk[0] == '0') ? 0 : 1;      // A/B switches for tests and profiling
+    if (const char* bk = getenv("TNSB_BUILD")) c->opt_build = (bk[0] == '1') ? 1 : 0;
     for (int k = 0; k < EV_COUNT; k++) cudaEventCreate(&c->ev[k]);
     *out = c;
     return TNSB_OK;
@@ -907,6 +951,9 @@ int tnsb_set_option(tnsb_context* c, int option, int64_t value)
     case TNSB_OPT_QUERY_LIMIT: c->opt_query_limit = value; return TNSB_OK;
     case TNSB_OPT_SORT_LISTS: c->opt_sort_lists = value != 0; return TNSB_OK;
     case TNSB_OPT_ZERO_COPY_RESULTS: c->opt_zero_copy = value != 0; return TNSB_OK;
+    case TNSB_OPT_BUILD:
+        if (value != 0 && value != 1) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: build must be 0 (automatic) or 1 (radix sort).");
+        c->opt_build = (int)value; return TNSB_OK;
     case TNSB_OPT_QUERY_KERNEL:
         if (value != 0 && value != 1) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: query kernel must be 0 (cell kernel) or 1 (round kernel).");
         c->opt_query_kernel = (int)value; return TNSB_OK;
@@ -990,13 +1037,13 @@ int tnsb_prepare_zsort(tnsb_context* c)
     TNSB_CUDA(c, cudaSetDevice(c->device));
     bool all_valid = true;
     int64_t n_total = 0;
-    for (auto& st : c->sets) { all_valid = all_valid && (st.sorted_valid || st.n == 0); n_total += st.n; }
+    for (auto& st : c->sets) { all_valid = all_valid && ((st.sorted_valid && st.order_valid) || st.n == 0); n_total += st.n; }
     if ((!all_valid || c->grid_row_mode) && n_total > 0) {
-        // no grid of the current points yet (TreeNSearch.cpp:2592-2595), or a grid in row-key order: the order handed to the user
-        // is the libmorton Z-order, so sort by 3-D Morton keys now
+        // no grid of the current points yet (TreeNSearch.cpp:2592-2595), or a grid without a stable Morton permutation (bucket build,
+        // row-key order): the order handed to the user is the libmorton Z-order, stable inside a cell, so radix sort by Morton keys now
         GridParams gp;
         memset(&c->stats, 0, sizeof(c->stats));
-        rc = build_grid(c, &gp, false);
+        rc = build_grid(c, &gp, false, true);
         if (rc != TNSB_OK) return rc;
     }
     for (auto& st : c->sets) {
