@@ -202,16 +202,17 @@ __global__ void __launch_bounds__(256) dense_table_kernel(const Key* __restrict_
 // Bucket build: when the cell table (one counter per cell of the whole grid) is small next to the point count, the sort of
 // (cell key, index) pairs collapses into ONE counting pass over the full key -- histogram, exclusive scan, scatter -- instead
 // of ceil(key_bits / 8) LSD radix passes, and the scatter writes the reordered float4 records directly (no separate gather).
-//   keygen_count_kernel   key of every point + its rank inside its cell = old value of the cell's population counter (ONE L2 atomic
-//                         per point on an L2 resident table)
+//   keygen_count_kernel   key of every point + population of its cell (fire-and-forget L2 atomics on an L2 resident table)
 //   exclusive_scan_u32    first[k] = number of points with a smaller key, for every k in [0, 2^key_bits]
-//   bucket_scatter_kernel sorted[first[key] + rank] = (x, y, z, bits(index)): a plain scatter, no second round of atomics
+//   bucket_scatter_kernel sorted[cursor[key]++] = (x, y, z, bits(index)); cursor starts as a copy of first.  (Measured: taking the rank
+//                         from a value-returning atomic in the first kernel instead is slower -- the scatter is bound by its random
+//                         16-byte writes, not by its atomics, and returning atomics cost 35 us more in keygen.)
 //   table_count/emit      compact list of the occupied cells (the query's task list) + the cell kernel's {start, end} table
 // The order of the points INSIDE a cell is the arrival order of the atomics (not the input order as with the stable radix
 // sort); neighbour SETS do not depend on it.  prepare_zsort() and TNSB_OPT_BUILD = 1 use the radix path.
 template <typename Key>
 __global__ void __launch_bounds__(256) keygen_count_kernel(const float* __restrict__ pts, int n, int stride, GridParams g, Key* __restrict__ keys, int row_order,
-                                                           uint32_t* __restrict__ population, uint32_t* __restrict__ rank)
+                                                           uint32_t* __restrict__ population)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -225,19 +226,24 @@ __global__ void __launch_bounds__(256) keygen_count_kernel(const float* __restri
     cz = min(max(cz, 0), g.max_coord);
     const Key k = row_order ? RowKey<Key>::encode((uint32_t)cx, (uint32_t)cy, (uint32_t)cz, g.bits) : Morton<Key>::encode((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
     keys[i] = k;
-    rank[i] = atomicAdd(population + k, 1u);
+    atomicAdd(population + k, 1u);
 }
 
 template <typename Key>
 __global__ void __launch_bounds__(256) bucket_scatter_kernel(const float* __restrict__ pts, int stride, const float* __restrict__ radii, const Key* __restrict__ keys,
-                                                             int n, const uint32_t* __restrict__ first, const uint32_t* __restrict__ rank, float4* __restrict__ sorted,
-                                                             float* __restrict__ sorted_r2)
+                                                             int n, uint32_t* __restrict__ cursor, float4* __restrict__ sorted, float* __restrict__ sorted_r2,
+                                                             Key key_lo, Key key_hi)
 {
+    // [key_lo, key_hi): destination window of this launch.  Random 16-byte writes over a 160 MB output miss L2 and make DRAM
+    // read-modify-write half sectors (ncu: 374 MB read + 287 MB written for 160 MB of records); with a window that fits L2 both
+    // halves of a sector meet there.  Measured at 10M points: 1 window 0.319 ms, 2 windows 0.271 ms, 4: 0.286 ms, 8: 0.427 ms.
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const Key k = keys[i];
+    if (k < key_lo || k >= key_hi) return;
     const float* p = pts + (int64_t)i * stride;
     const float x = p[0], y = p[1], z = p[2];
-    const uint32_t pos = first[keys[i]] + rank[i];
+    const uint32_t pos = atomicAdd(cursor + k, 1u);
     sorted[pos] = make_float4(x, y, z, __uint_as_float((uint32_t)i));
     if (radii) {
         const float r = radii[i];

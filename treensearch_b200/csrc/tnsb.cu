@@ -97,6 +97,7 @@ struct SetState {
     int dense_cells = 0;           // cells of the previous run whose entries are still set
     bool use_dense = false;
     DevBuf first;                  // prefix cell table first[key] for every key in [0, 2^key_bits] (+ scan scratch behind it): bucket build, row-key mode
+    DevBuf cursor;                 // bucket build: next free slot of every cell during the scatter
     bool use_table = false;
     bool bucket = false;           // the last build of this set was a bucket build (no sorted permutation in vals[])
     bool order_valid = false;      // vals[sel] holds the stable sorted permutation of the last build
@@ -150,6 +151,7 @@ struct tnsb_context {
     bool opt_sort_lists = false;
     bool opt_zero_copy = true;
     int opt_point_stride = 3;
+    int opt_bucket_passes = 0;          // 0: automatic
     int opt_build = 0;             // 0: bucket build when the cell table is small enough, else radix sort; 1: always radix sort
     int opt_query_kernel = 0;      // 0: query_kernel (candidates in registers, lane = candidate; Morton keys), 1: query_rounds_kernel (lane = query; row keys)
 
@@ -256,14 +258,14 @@ int build_sets(tnsb_context* c, const GridParams& gp, bool row_mode, bool need_o
         if (st.n == 0) continue;
         for (int b = 0; b < (st.bucket ? 1 : 2); b++) {
             TNSB_CUDA(c, st.keys[b].ensure(sizeof(Key) * (size_t)st.n, 1.1));
-            TNSB_CUDA(c, st.vals[b].ensure(sizeof(uint32_t) * (size_t)st.n, 1.1));       // bucket build: vals[0] = rank of the point inside its cell
+            if (!st.bucket) TNSB_CUDA(c, st.vals[b].ensure(sizeof(uint32_t) * (size_t)st.n, 1.1));
         }
         if (st.bucket) {
             const int64_t n_entries = n_keys + 1;
             TNSB_CUDA(c, st.first.ensure(sizeof(uint32_t) * (size_t)(n_entries + exclusive_scan_temp_elems(n_entries))));
+            TNSB_CUDA(c, st.cursor.ensure(sizeof(uint32_t) * (size_t)n_keys));
             TNSB_CUDA(c, cudaMemsetAsync(st.first.p, 0, sizeof(uint32_t) * (size_t)n_entries, s));
-            keygen_count_kernel<Key><<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.n, st.d_stride, gp, st.keys[0].as<Key>(), row_mode ? 1 : 0, st.first.as<uint32_t>(),
-                                                                        st.vals[0].as<uint32_t>());
+            keygen_count_kernel<Key><<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.n, st.d_stride, gp, st.keys[0].as<Key>(), row_mode ? 1 : 0, st.first.as<uint32_t>());
         } else {
             keygen_kernel<Key><<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.n, st.d_stride, gp, st.keys[0].as<Key>(), row_mode ? 1 : 0);
         }
@@ -277,6 +279,7 @@ int build_sets(tnsb_context* c, const GridParams& gp, bool row_mode, bool need_o
             const int64_t n_entries = n_keys + 1;
             uint32_t* first = st.first.as<uint32_t>();
             launches += exclusive_scan_u32(first, first, n_entries, first + n_entries, nullptr, s);
+            TNSB_CUDA(c, cudaMemcpyAsync(st.cursor.p, first, sizeof(uint32_t) * (size_t)n_keys, cudaMemcpyDeviceToDevice, s));
             c->stats.sort_passes = std::max(c->stats.sort_passes, 1);
         } else {
             TNSB_CUDA(c, c->sort_temp.ensure(sizeof(uint32_t) * (size_t)radix_sort_temp_elems<Key>(st.n), 1.1));
@@ -294,11 +297,16 @@ int build_sets(tnsb_context* c, const GridParams& gp, bool row_mode, bool need_o
         if (st.n == 0) continue;
         TNSB_CUDA(c, st.sorted.ensure(sizeof(float4) * (size_t)st.n, 1.1));
         if (st.has_radii) TNSB_CUDA(c, st.sorted_r2.ensure(sizeof(float) * (size_t)st.n, 1.1));
-        if (st.bucket)
-            bucket_scatter_kernel<Key><<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.d_stride, st.has_radii ? st.d_radii : nullptr, st.keys[0].as<Key>(), st.n,
-                                                                          st.first.as<uint32_t>(), st.vals[0].as<uint32_t>(), st.sorted.as<float4>(),
-                                                                          st.sorted_r2.as<float>());
-        else
+        if (st.bucket) {
+            // destination windows of <= 80 MB of records (L2 is 126 MB): see bucket_scatter_kernel
+            int passes = c->opt_bucket_passes > 0 ? c->opt_bucket_passes : (int)std::min<int64_t>(16, std::max<int64_t>(1, ((int64_t)st.n * 16 + (80ll << 20) - 1) / (80ll << 20)));
+            for (int p = 0; p < passes; p++) {
+                const Key lo = (Key)(n_keys * p / passes), hi = (Key)(n_keys * (p + 1) / passes);
+                bucket_scatter_kernel<Key><<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.d_stride, st.has_radii ? st.d_radii : nullptr, st.keys[0].as<Key>(), st.n,
+                                                                              st.cursor.as<uint32_t>(), st.sorted.as<float4>(), st.sorted_r2.as<float>(), lo, hi);
+            }
+            launches += passes - 1;
+        } else
             reorder_kernel<<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.d_stride, st.has_radii ? st.d_radii : nullptr, st.vals[st.sel].as<uint32_t>(), st.n,
                                                               st.sorted.as<float4>(), st.sorted_r2.as<float>());
         launches++;
@@ -795,6 +803,7 @@ int tnsb_create(tnsb_context** out, int device)
     c->own_stream = c->stream;
     if (const char* qk = getenv("TNSB_QUERY_KERNEL")) c->opt_query_kernel = (qk[0] == '0') ? 0 : 1;      // A/B switches for tests and profiling
     if (const char* bk = getenv("TNSB_BUILD")) c->opt_build = (bk[0] == '1') ? 1 : 0;
+    if (const char* bp = getenv("TNSB_BUCKET_PASSES")) c->opt_bucket_passes = atoi(bp);
     for (int k = 0; k < EV_COUNT; k++) cudaEventCreate(&c->ev[k]);
     *out = c;
     return TNSB_OK;
@@ -810,7 +819,7 @@ void tnsb_destroy(tnsb_context* c)
         st.up_pts.release(); st.up_radii.release(); st.cv_pts.release(); st.cv_radii.release();
         for (int b = 0; b < 2; b++) { st.keys[b].release(); st.vals[b].release(); }
         st.sorted.release(); st.sorted_r2.release(); st.cell_key.release(); st.cell_start.release(); st.tile_heads.release();
-        st.htable.release(); st.dense.release(); st.first.release(); st.d_zorder.release();
+        st.htable.release(); st.dense.release(); st.first.release(); st.cursor.release(); st.d_zorder.release();
     }
     for (auto& p : c->pairs) { p.d_ragged.release(); p.d_list_pos.release(); p.h_ragged.release(); p.h_list_pos.release(); }
     c->d_reduce.release(); c->d_counters.release(); c->d_misc.release(); c->sort_temp.release(); c->scan_temp.release(); c->h_small.release();
