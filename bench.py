@@ -161,6 +161,9 @@ def workload_config(args, total):
             "dambreak": "SPH dam-break clustered points (~60 neighbours interior), single set, fixed radius"}[args.workload]
     return {"workload": f"{total} {name}" + (f", Z-slab sharded over {args.gpus} GPUs with NCCL halo exchange" if args.gpus > 1 else ", 1xB200"),
             "n_points": total, "points_per_gpu": args.points_per_gpu, "active_searches": "0->0",
+            **({"shard_input": {"slab": "every rank holds its own Z slab (halo + migrating points exchanged per step)",
+                                "random": "every rank holds an i.i.d. sample of the whole cube (full redistribution per step)"}[args.shard_input]}
+               if args.gpus > 1 else {}),
             "l2": "flushed between timed steps (256 MiB write, untimed); per-step working set ~1.9 GB >> 126 MB L2"}
 
 
@@ -215,7 +218,7 @@ def run_ours(args):
         stats_e2e = eng_e2e.stats
     else:
         from treensearch_b200 import sharded
-        job = sharded.ShardedUniformJob(args.workload, args.points_per_gpu, rank, world, local_rank, stream)
+        job = sharded.ShardedUniformJob(args.workload, args.points_per_gpu, rank, world, local_rank, stream, args.shard_input)
         r = job.radius
         n_local = args.points_per_gpu
         step_dev = job.step_device
@@ -332,6 +335,9 @@ def main():
     ap.add_argument("--points-per-gpu", type=int, default=10_000_000)
     ap.add_argument("--workload", choices=["uniform", "dambreak"], default="uniform")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard-input", choices=["slab", "random"], default="slab",
+                    help="multi-GPU only: every rank starts with its own Z slab of the cloud (default; a step exchanges halo + migrants) "
+                         "or with an i.i.d. sample of the whole cube (every step redistributes (N-1)/N of all points)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

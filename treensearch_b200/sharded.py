@@ -200,7 +200,7 @@ class ShardedSearch:
 class ShardedUniformJob:
     """bench.py helper: this rank's 1/world chunk of a synthetic cloud, stepped device-resident or end-to-end."""
 
-    def __init__(self, workload, points_per_gpu, rank, world, local_rank, stream):
+    def __init__(self, workload, points_per_gpu, rank, world, local_rank, stream, shard_input="slab"):
         import torch
         import torch.distributed as dist
         from . import clouds
@@ -209,6 +209,12 @@ class ShardedUniformJob:
             raise SystemExit("multi-GPU bench supports the uniform workload")
         self.radius = float(clouds.radius_for_mean_neighbors(total))
         chunk = clouds.uniform_cloud(points_per_gpu, 42 + rank)          # i.i.d. uniform chunk of the global cloud
+        if shard_input == "slab":
+            # the cloud is ALREADY sharded by Z slab, as in a running simulation: rank r holds z in [r/world, (r+1)/world).  A step then
+            # exchanges the one-cell halo plus the few points that the count-balanced cuts move across a boundary.  "random" hands
+            # every rank an i.i.d. sample of the whole cube instead: (world-1)/world of all points change rank in every step.
+            chunk = chunk.copy()
+            chunk[:, 2] = (chunk[:, 2] + np.float32(rank)) / np.float32(world)
         self.h_pts = torch.from_numpy(chunk).pin_memory()
         self.d_pts = self.h_pts.cuda(non_blocking=False)
         self.d_stage = torch.empty_like(self.d_pts)
