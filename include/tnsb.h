@@ -185,6 +185,22 @@ int tnsb_shard_histogram(tnsb_context* ctx, const float* d_points, int n_points,
 int tnsb_shard_partition(tnsb_context* ctx, const float* d_points, int n_points, int stride, int id_base, int axis,
                          const float* cuts, int n_parts, float halo, float* d_records, int64_t capacity_records, int64_t* counts_out);
 
+/* One-sided exchange over peer memory (NVLink / NVSwitch): partition + exchange in ONE kernel, no count pass, no all-to-all.
+   Every rank (one process per GPU) creates two receive windows in its HBM (step parity), publishes their CUDA IPC handles
+   (2 x 64 bytes; exchange them with any host side all-gather) and opens the windows of all ranks.  Per step:
+       tnsb_shard_push(parity)    routes every local point into its owner's window and into the windows that need it as halo
+       <barrier across the ranks, stream ordered behind the push: e.g. a 4-byte NCCL all_reduce(MAX) of d_flag>
+       tnsb_shard_collect(parity) -> device pointer to this rank's [owned | halo] (x, y, z, bits(global id)) records and their counts;
+                                     feed it to tnsb_resize_point_set_f32 with TNSB_OPT_POINT_STRIDE = 4, TNSB_OPT_QUERY_LIMIT = n_owned.
+   Alternate parity 0 / 1 from step to step: peers may already push step k+1 while this rank still searches step k.
+   d_flag >= 2 after the barrier (and TNSB_ERR_LIMIT from the owner's collect): a window was too small -- the counts returned by
+   collect are exact: all ranks create larger windows and repeat the step. */
+int tnsb_shard_window_create(tnsb_context* ctx, int64_t capacity_owned_records, int64_t capacity_halo_records, unsigned char* ipc_handles_out /* 128 bytes */);
+int tnsb_shard_window_open(tnsb_context* ctx, int n_ranks, int my_rank, const unsigned char* all_ipc_handles /* n_ranks x 128 bytes, rank major */);
+int tnsb_shard_push(tnsb_context* ctx, int parity, const float* d_points, int n_points, int stride, int id_base, int axis,
+                    const float* cuts, int n_parts, float halo, int* d_flag /* device int, raised to 2 when a window overflows; may be NULL */);
+int tnsb_shard_collect(tnsb_context* ctx, int parity, float** d_records, int64_t* n_owned, int64_t* n_halo);
+
 /* ---- diagnostics ---------------------------------------------------------------------------------------------------- */
 /* replaces: get_neighborlist_n_bytes()  TreeNSearch.h:246 / .cpp:254-261 */
 uint64_t tnsb_get_neighborlist_n_bytes(const tnsb_context* ctx);

@@ -172,6 +172,12 @@ struct tnsb_context {
     std::map<const void*, size_t> registered;
     tnsb_stats stats;
 
+    // one-sided multi-GPU exchange (tnsb_shard_window_*): two receive windows (step parity) + the peers' windows mapped through CUDA IPC
+    DevBuf win[2];
+    int64_t win_cap_owned = 0, win_cap_halo = 0;
+    int win_ranks = 0, win_rank = -1;
+    std::vector<void*> win_peer[2];
+
     tnsb_context() { memset(&stats, 0, sizeof(stats)); }
 };
 
@@ -822,6 +828,11 @@ void tnsb_destroy(tnsb_context* c)
         st.htable.release(); st.dense.release(); st.first.release(); st.cursor.release(); st.d_zorder.release();
     }
     for (auto& p : c->pairs) { p.d_ragged.release(); p.d_list_pos.release(); p.h_ragged.release(); p.h_list_pos.release(); }
+    for (int p = 0; p < 2; p++) {
+        for (int r = 0; r < (int)c->win_peer[p].size(); r++)
+            if (r != c->win_rank && c->win_peer[p][r]) cudaIpcCloseMemHandle(c->win_peer[p][r]);
+        c->win[p].release();
+    }
     c->d_reduce.release(); c->d_counters.release(); c->d_misc.release(); c->sort_temp.release(); c->scan_temp.release(); c->h_small.release();
     for (int k = 0; k < EV_COUNT; k++) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -1162,6 +1173,109 @@ int tnsb_shard_partition(tnsb_context* c, const float* d_points, int n, int stri
     if (n > 0) slab_scatter_kernel<<<grid, kShardThreads, 0, c->stream>>>(d_points, n, stride, axis, id_base, sc, d_cursors, reinterpret_cast<float4*>(d_records));
     TNSB_CUDA(c, cudaGetLastError());
     TNSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TNSB_OK;
+}
+
+// ---- one-sided exchange over peer memory -------------------------------------------------------------------------------
+int tnsb_shard_window_create(tnsb_context* c, int64_t cap_owned, int64_t cap_halo, unsigned char* handles_out)
+{
+    if (!c || !handles_out || cap_owned < 1 || cap_halo < 1) return TNSB_ERR_INVALID_ARGUMENT;
+    TNSB_CUDA(c, cudaSetDevice(c->device));
+    TNSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int p = 0; p < 2; p++) {
+        for (int r = 0; r < (int)c->win_peer[p].size(); r++)
+            if (r != c->win_rank && c->win_peer[p][r]) cudaIpcCloseMemHandle(c->win_peer[p][r]);
+        c->win_peer[p].clear();
+        c->win[p].release();
+        const size_t bytes = kWindowHeaderBytes + sizeof(float4) * (size_t)(cap_owned + cap_halo);
+        TNSB_CUDA(c, c->win[p].ensure(bytes));
+        TNSB_CUDA(c, cudaMemset(c->win[p].p, 0, kWindowHeaderBytes));
+        cudaIpcMemHandle_t h;
+        TNSB_CUDA(c, cudaIpcGetMemHandle(&h, c->win[p].p));
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        memcpy(handles_out + 64 * p, &h, 64);
+    }
+    c->win_cap_owned = cap_owned;
+    c->win_cap_halo = cap_halo;
+    c->win_ranks = 0;
+    c->win_rank = -1;
+    return TNSB_OK;
+}
+
+int tnsb_shard_window_open(tnsb_context* c, int n_ranks, int my_rank, const unsigned char* all_handles)
+{
+    if (!c || !all_handles || n_ranks < 1 || n_ranks > kMaxParts || my_rank < 0 || my_rank >= n_ranks) return TNSB_ERR_INVALID_ARGUMENT;
+    if (!c->win[0].p) return fail(c, TNSB_ERR_INVALID_STATE, "tnsb_shard_window_open: create the window first.");
+    TNSB_CUDA(c, cudaSetDevice(c->device));
+    for (int p = 0; p < 2; p++) {
+        c->win_peer[p].assign((size_t)n_ranks, nullptr);
+        for (int r = 0; r < n_ranks; r++) {
+            if (r == my_rank) { c->win_peer[p][r] = c->win[p].p; continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, all_handles + ((size_t)r * 2 + p) * 64, 64);
+            void* ptr = nullptr;
+            TNSB_CUDA(c, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+            c->win_peer[p][r] = ptr;
+        }
+    }
+    c->win_ranks = n_ranks;
+    c->win_rank = my_rank;
+    return TNSB_OK;
+}
+
+int tnsb_shard_push(tnsb_context* c, int parity, const float* d_points, int n, int stride, int id_base, int axis, const float* cuts, int n_parts, float halo,
+                    int* d_flag)
+{
+    if (!c || !cuts || axis < 0 || axis > 2 || (stride != 3 && stride != 4) || parity < 0 || parity > 1) return TNSB_ERR_INVALID_ARGUMENT;
+    if (c->win_ranks < 1 || n_parts != c->win_ranks) return fail(c, TNSB_ERR_INVALID_STATE, "tnsb_shard_push: windows are not open for this number of ranks.");
+    TNSB_CUDA(c, cudaSetDevice(c->device));
+    SlabCuts sc;
+    sc.n_parts = n_parts;
+    sc.halo = halo;
+    for (int k = 0; k <= n_parts; k++) sc.cut[k] = cuts[k];
+    PushWindows w;
+    memset(&w, 0, sizeof(w));
+    for (int r = 0; r < n_parts; r++) w.base[r] = static_cast<char*>(c->win_peer[parity][r]);
+    w.cap_owned = c->win_cap_owned;
+    w.cap_halo = c->win_cap_halo;
+    if (n > 0) {
+        if (!is_device_pointer(d_points)) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb_shard_push: points must be device memory.");
+        slab_push_kernel<<<4 * c->n_sms, kShardThreads, 0, c->stream>>>(d_points, n, stride, axis, id_base, sc, w, d_flag);
+        TNSB_CUDA(c, cudaGetLastError());
+    }
+    return TNSB_OK;
+}
+
+int tnsb_shard_collect(tnsb_context* c, int parity, float** d_records, int64_t* n_owned, int64_t* n_halo)
+{
+    if (!c || !d_records || !n_owned || !n_halo || parity < 0 || parity > 1) return TNSB_ERR_INVALID_ARGUMENT;
+    if (c->win_ranks < 1) return fail(c, TNSB_ERR_INVALID_STATE, "tnsb_shard_collect: windows are not open.");
+    TNSB_CUDA(c, cudaSetDevice(c->device));
+    TNSB_CUDA(c, c->h_small.ensure(4096));
+    unsigned long long* h = reinterpret_cast<unsigned long long*>(c->h_small.as<char>() + 3072);
+    TNSB_CUDA(c, cudaMemcpyAsync(h, c->win[parity].p, 16, cudaMemcpyDeviceToHost, c->stream));
+    TNSB_CUDA(c, cudaMemsetAsync(c->win[parity].p, 0, 16, c->stream));     // ready for the step after next (peers wait for the next barrier)
+    TNSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    const int64_t no = (int64_t)h[0], nh = (int64_t)h[1];
+    *n_owned = no;
+    *n_halo = nh;
+    *d_records = reinterpret_cast<float*>(c->win[parity].as<char>() + kWindowHeaderBytes);
+    if (no > c->win_cap_owned || nh > c->win_cap_halo)
+        return fail(c, TNSB_ERR_LIMIT, "tnsb_shard_collect: receive window too small (" + std::to_string(no) + " owned, " + std::to_string(nh) + " halo records).");
+    // halo records right behind the owned ones: [owned | halo] is what TNSB_OPT_QUERY_LIMIT expects
+    if (nh > 0 && no < c->win_cap_owned) {
+        float* dst = *d_records + 4 * no;
+        float* src = *d_records + 4 * c->win_cap_owned;
+        const size_t bytes = sizeof(float4) * (size_t)nh;
+        if (no + nh <= c->win_cap_owned) {
+            TNSB_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream));
+        } else {
+            // source and destination overlap: through a scratch buffer
+            TNSB_CUDA(c, c->scan_temp.ensure(bytes, 1.1));
+            TNSB_CUDA(c, cudaMemcpyAsync(c->scan_temp.p, src, bytes, cudaMemcpyDeviceToDevice, c->stream));
+            TNSB_CUDA(c, cudaMemcpyAsync(dst, c->scan_temp.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+        }
+    }
     return TNSB_OK;
 }
 

@@ -12,6 +12,13 @@ The reference is a single shared-memory process; this decomposition is new desig
      query needs, so there is no second exchange.
   5. the single-GPU engine on [owned | halo] records with TNSB_OPT_QUERY_LIMIT = n_owned: halo points are find-only.
 
+Steps 3 + 4 exist in two forms (`exchange=`):
+  "nccl"  two partition kernels, all_to_all of the counts, all_to_all_single of the owned and of the halo records;
+  "p2p"   (default on CUDA with world > 1) ONE kernel pushes every record straight into its owner's receive window -- and into
+          the windows that need it as halo -- over NVLink peer memory (CUDA IPC, tnsb_shard_window_* / tnsb_shard_push), followed
+          by a 4-byte all_reduce that is both the barrier and the carrier of the re-balance flag.  No count pass, no count
+          exchange, no all-to-all; the engine then searches the records in place in the window.
+
 Neighbour lists come back in LOCAL indices (into the rank's [owned | halo] array, which is what a distributed consumer
 indexes anyway); `local_ids` maps them to global point ids.  No data-path collective other than step 4 exists.
 
@@ -83,11 +90,18 @@ def exchange_records(dist, records, counts: np.ndarray, world: int, flag: int = 
     return local, n_owned, n_halo, int(rc[:, 2].max())
 
 
+class _DeviceRecords:
+    """(n, 4) float32 view of device memory owned by the engine (a receive window), exposed through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (int(n), 4), "typestr": "<f4", "data": (int(ptr), False), "version": 3, "strides": None}
+
+
 class ShardedSearch:
     """One rank of the Z-slab sharded fixed-radius search.  `dist` is torch.distributed (already initialised) or None."""
 
     def __init__(self, radius: float, rank: int = 0, world: int = 1, device: int = 0, axis: int = 2, n_bins: int = 4096,
-                 stream=None, dist=None):
+                 stream=None, dist=None, exchange: str = "auto"):
         import torch
         from .api import TreeNSearch
         self.torch = torch
@@ -112,6 +126,58 @@ class ShardedSearch:
         self.n_global = 0
         self._recut = True
         self.n_recuts = 0
+        # one-sided exchange over peer memory needs one process per GPU talking NCCL; everything else uses the collective form
+        if exchange == "auto":
+            exchange = "p2p" if (dist is not None and world > 1 and dist.get_backend() == "nccl") else "nccl"
+        self.exchange = exchange
+        self._win_caps = None
+        self._step_no = 0
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    # ---- one-sided exchange (tnsb_shard_window_*)
+    def _open_windows(self, cap_owned: int, cap_halo: int):
+        """Same capacities on every rank (the pushers check them); collective."""
+        torch, dist = self.torch, self.dist
+        caps = torch.tensor([int(cap_owned), int(cap_halo)], dtype=torch.int64, device=self.device)
+        dist.all_reduce(caps, op=dist.ReduceOp.MAX)          # also: every rank is done with the old windows
+        cap_owned, cap_halo = (int(v) for v in caps.cpu().tolist())
+        mine = (C.c_ubyte * 128)()
+        self.engine._check(self.engine._lib.tnsb_shard_window_create(self.engine._h, cap_owned, cap_halo, mine))
+        h = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=self.device)
+        allh = torch.empty(self.world * 128, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(allh, h)
+        buf = (C.c_ubyte * (self.world * 128))(*allh.cpu().tolist())
+        self.engine._check(self.engine._lib.tnsb_shard_window_open(self.engine._h, self.world, self.rank, buf))
+        dist.barrier()                       # nobody pushes before every rank has mapped every window
+        self._win_caps = (cap_owned, cap_halo)
+        self._step_no = 0
+
+    def _push_exchange(self, points, id_base, want):
+        """Partition + exchange as one kernel over peer memory.  Returns (local records view, n_owned, n_halo, flag)."""
+        torch, dist = self.torch, self.dist
+        n = int(points.shape[0])
+        if self._win_caps is None:
+            self._open_windows(int(n * 1.5) + 4096, int(n * 0.5) + 4096)
+        cuts_c = (C.c_float * (self.world + 1))(*[float(c) if np.isfinite(c) else 0.0 for c in self.cuts])
+        for _attempt in range(4):
+            parity = self._step_no & 1
+            self._step_no += 1
+            self._flag.fill_(int(want))
+            self.engine._check(self.engine._lib.tnsb_shard_push(self.engine._h, parity, points.data_ptr(), n, int(points.shape[1]), int(id_base), self.axis,
+                                                              cuts_c, self.world, float(halo_width(self.radius)), self._flag.data_ptr()))
+            dist.all_reduce(self._flag, op=dist.ReduceOp.MAX)       # barrier (stream ordered behind the push) + re-balance / overflow flag
+            ptr, n_owned, n_halo = C.c_void_p(), C.c_int64(), C.c_int64()
+            rc = self.engine._lib.tnsb_shard_collect(self.engine._h, parity, C.byref(ptr), C.byref(n_owned), C.byref(n_halo))
+            flag = int(self._flag.item())
+            if flag < 2:
+                self.engine._check(rc)
+                local = torch.as_tensor(_DeviceRecords(ptr.value, n_owned.value + n_halo.value), device=self.device)
+                return local, int(n_owned.value), int(n_halo.value), flag
+            # a window overflowed somewhere: EVERY rank repeats the step with larger windows (the counts are exact)
+            if rc not in (L.TNSB_OK, L.TNSB_ERR_LIMIT):
+                self.engine._check(rc)
+            self._open_windows(int(n_owned.value * 1.25) + 4096, int(n_halo.value * 1.5) + 4096)
+        raise RuntimeError("sharded search: receive windows kept overflowing")
 
     # ---- thin wrappers of the shard helpers of the C ABI
     def _aabb(self, pts):
@@ -162,12 +228,15 @@ class ShardedSearch:
             self.cuts = balanced_cuts(hist, lo, hi, self.world)
             self.n_recuts += 1
         # 3. partition, 4. exchange (cut coordinates are open ended at both ends, so points that left the old box still have an owner)
-        counts = self._partition(points, id_base, self.cuts, halo_width(self.radius))
         want = 0
         if self.n_global > 0 and self.n_owned > 0:
             mean = self.n_global / self.world
             want = int(abs(self.n_owned - mean) > self.rebalance_tolerance * mean)     # judged on the previous step's balance
-        self.local, self.n_owned, self.n_halo, flag = exchange_records(dist, self._records, counts, self.world, want)
+        if self.exchange == "p2p":
+            self.local, self.n_owned, self.n_halo, flag = self._push_exchange(points, id_base, want)
+        else:
+            counts = self._partition(points, id_base, self.cuts, halo_width(self.radius))
+            self.local, self.n_owned, self.n_halo, flag = exchange_records(dist, self._records, counts, self.world, want)
         self._recut = bool(flag)
         # 5. local search, halo points find-only
         eng = self.engine
