@@ -1,0 +1,4 @@
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -6 | tee gpurun_out/full.log
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -c 400 gpurun_out/bench_default.err
+timeout 600 python bench.py --steps 5 --warmup 3 --workload dambreak --no-cpu-baseline > gpurun_out/bench_dambreak.json 2> gpurun_out/bench_dambreak.err; tail -c 400 gpurun_out/bench_dambreak.err

@@ -244,19 +244,25 @@ int validate(tnsb_context* c)
     return TNSB_OK;
 }
 
+// ext[d]: largest cell coordinate on axis d that a point OR one of its neighbour cells can have (occupied extent + margin, clamped
+// to the grid).  Keys above encode(ext) cannot occur, so the cell tables only cover [0, encode(ext)]: a flat or elongated cloud
+// (dam-break tank, a Z slab of a sharded cloud) gets a table that matches its extent instead of the cubic power-of-two grid.
 template <typename Key>
-int build_sets(tnsb_context* c, const GridParams& gp, bool row_mode, bool need_order)
+int build_sets(tnsb_context* c, const GridParams& gp, bool row_mode, bool need_order, const int ext[3])
 {
     cudaStream_t s = c->stream;
     int& launches = c->stats.n_kernel_launches;
     const int key_bits = 3 * gp.bits;
     const int n_sets = (int)c->sets.size();
-    const int64_t n_keys = key_bits <= 40 ? (1ll << key_bits) : -1;
+    const int64_t n_keys = sizeof(Key) == 4
+        ? (int64_t)(row_mode ? RowKey<Key>::encode((uint32_t)ext[0], (uint32_t)ext[1], (uint32_t)ext[2], gp.bits)
+                             : Morton<Key>::encode((uint32_t)ext[0], (uint32_t)ext[1], (uint32_t)ext[2])) + 1
+        : -1;
     // Per set: bucket build (one counting pass over the full cell key, see grid_build.cuh) while the cell table is small next to the
     // point count, else -- huge sparse domains, 64-bit keys, prepare_zsort (needs the stable permutation), TNSB_OPT_BUILD = 1 -- the LSD
     // radix sort of (key, index) pairs.
     for (auto& st : c->sets) {
-        st.bucket = !need_order && c->opt_build == 0 && st.n > 0 && sizeof(Key) == 4 && key_bits <= 26 && n_keys <= std::max<int64_t>(1ll << 22, 4ll * st.n);
+        st.bucket = !need_order && c->opt_build == 0 && st.n > 0 && n_keys > 0 && n_keys <= (1ll << 27) && n_keys <= std::max<int64_t>(1ll << 22, 4ll * st.n);
         st.order_valid = false;
     }
     // ---- cell assignment + keys (+ cell populations)
@@ -342,14 +348,14 @@ int build_sets(tnsb_context* c, const GridParams& gp, bool row_mode, bool need_o
         //   row keys (round kernel): prefix table first[key] over ALL cells while that is affordable, else a hash of the occupied cells;
         //   Morton keys (cell kernel): dense Morton-indexed {start, end} table while the grid has <= 2^27 cells, else the hash
         //   (open addressing at <= 33% load, 16-byte slots {key, start, end}).
-        st.use_table = row_mode && (st.bucket || (key_bits <= 26 && n_keys <= std::max<int64_t>(1ll << 22, 8ll * st.n)));
-        st.use_dense = !row_mode && key_bits <= 27;
+        st.use_table = row_mode && (st.bucket || (n_keys > 0 && n_keys <= (1ll << 26) && n_keys <= std::max<int64_t>(1ll << 22, 8ll * st.n)));
+        st.use_dense = !row_mode && (st.bucket || key_bits <= 27);
         if (st.use_table && !st.bucket) {
             const int64_t n_entries = n_keys + 1;
             TNSB_CUDA(c, st.first.ensure(sizeof(uint32_t) * (size_t)(n_entries + exclusive_scan_temp_elems(n_entries))));
             TNSB_CUDA(c, cudaMemsetAsync(st.first.p, 0, sizeof(uint32_t) * (size_t)n_entries, s));
         } else if (st.use_dense) {
-            const size_t dbytes = sizeof(uint2) << key_bits;
+            const size_t dbytes = st.bucket ? sizeof(uint2) * (size_t)n_keys : sizeof(uint2) << key_bits;      // bucket build: every entry of [0, n_keys) is rewritten
             const bool fresh = st.dense.cap < dbytes || st.dense_bits != key_bits;
             TNSB_CUDA(c, st.dense.ensure(dbytes));
             if (st.bucket) {
@@ -573,11 +579,14 @@ int build_grid(tnsb_context* c, GridParams* gp_out, bool row_mode, bool need_ord
         while ((double)(1ll << bits) < n_cells_f && bits < 40) bits++;
         if (bits > Morton<uint64_t>::kMaxBits)
             return fail(c, TNSB_ERR_LIMIT, "TreeNSearch error: Max allowed cells per dimension is 2097152 (2^21); the search radius is too small for the extent of the point cloud.");
+        // The box is anchored just below the cloud's minimum corner (the reference centres it): occupied cells then start near
+        // coordinate 0 on every axis, so the largest key -- and with it the size of the cell tables -- follows the cloud's extent
+        // per axis instead of the cubic power-of-two grid (a 4:2:1 tank or a Z slab gets a table 5-8x smaller).
         const double full = cell * (double)(1ll << bits);
+        const double margin = 0.5 * (length - length / 1.1);        // half of the 10 % enlargement on the low side
         for (int d = 0; d < 3; d++) {
-            const double center = 0.5 * ((double)hi[d] + (double)lo[d]);
-            c->dom_bottom[d] = center - 0.5 * full;
-            c->dom_top[d] = center + 0.5 * full;
+            c->dom_bottom[d] = (double)lo[d] - margin;
+            c->dom_top[d] = c->dom_bottom[d] + full;
         }
         c->cell = cell;
         c->bits = bits;
@@ -594,8 +603,14 @@ int build_grid(tnsb_context* c, GridParams* gp_out, bool row_mode, bool need_ord
     c->stats.key_bits = 3 * c->bits;
     for (int d = 0; d < 3; d++) { c->stats.domain_bottom[d] = (float)c->dom_bottom[d]; c->stats.domain_top[d] = (float)c->dom_top[d]; }
 
+    // occupied extent in cells (same fp64 arithmetic as keygen) + 2 cells of margin: covers every neighbour cell a query can ask for
+    int ext[3];
+    for (int d = 0; d < 3; d++) {
+        const double mc = std::floor(((double)hi[d] - gp.bottom[d]) * gp.inv_cell);
+        ext[d] = (int)std::min<double>((double)gp.max_coord, std::max(0.0, mc) + 2.0);
+    }
     c->grid_row_mode = row_mode;
-    return c->key64 ? build_sets<uint64_t>(c, gp, row_mode, need_order) : build_sets<uint32_t>(c, gp, row_mode, need_order);
+    return c->key64 ? build_sets<uint64_t>(c, gp, row_mode, need_order, ext) : build_sets<uint32_t>(c, gp, row_mode, need_order, ext);
 }
 
 float ev_ms(tnsb_context* c, int a, int b)
