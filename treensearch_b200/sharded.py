@@ -128,6 +128,9 @@ class ShardedSearch:
         self.n_recuts = 0
         # one-sided exchange over peer memory needs one process per GPU talking NCCL; everything else uses the collective form
         if exchange == "auto":
+            import os
+            exchange = os.environ.get("TNSB_SHARD_EXCHANGE", "auto")      # "nccl" forces the collective form (e.g. ranks on several nodes)
+        if exchange == "auto":
             exchange = "p2p" if (dist is not None and world > 1 and dist.get_backend() == "nccl") else "nccl"
         self.exchange = exchange
         self._win_caps = None
