@@ -51,11 +51,12 @@ enum {
                                     memory (PCIe writes overlap the search, no HBM copy of the ids, no D2H afterwards; measured 28.1 ms
                                     vs 29.7 ms end to end at 10M points); 0 = lists in HBM, then one D2H copy.  Ignored (HBM path) when
                                     TNSB_OPT_SORT_LISTS is set or HOST_RESULTS is 0 */
-    TNSB_OPT_QUERY_KERNEL = 8,   /* which 27-cell query kernel runs: 0 (default) = query_kernel (grid sorted by 3-D Morton keys, a lane owns a
-                                    CANDIDATE, ballot compaction), 1 = query_rounds_kernel (grid sorted by row keys + prefix cell table, a lane
-                                    owns a QUERY, candidate tiles in shared memory, private hit lists).  Same neighbour sets; measured on B200
-                                    (DESIGN.md §4): kernel 0 is faster at 10M points (2.57 vs 2.98 ms uniform, 3.59 vs 5.01 ms dam-break).
-                                    The environment variable TNSB_QUERY_KERNEL=0|1 sets the default of new contexts */
+    TNSB_OPT_QUERY_KERNEL = 8,   /* which distance query runs: 0 (default) = automatic: the brick query (half-radius grid with linear row keys + prefix
+                                    cell table, slab rows staged by TMA bulk copies, a lane owns a QUERY; csrc/query_brick.cuh) while the cell table is
+                                    affordable (cells <= max(2^22, 8 x points)), else the cell kernel; 1 = always the cell kernel (cell = radius, 3-D
+                                    Morton keys, dense table or hash of the occupied cells, a lane owns a CANDIDATE, ballot compaction; csrc/query.cuh:
+                                    huge sparse domains, 64-bit keys).  Same neighbour sets.  TNSB_QUERY_KERNEL=0|1 in the environment sets the
+                                    default of new contexts */
     TNSB_OPT_BUILD = 9,          /* how the sorted grid is built: 0 (default) = automatic: a bucket build (ONE counting pass over the full cell
                                     key: cell populations by L2 atomics, exclusive scan, scatter of the (x, y, z, id) records) while the cell
                                     table is small next to the point count, else the LSD radix sort of (key, index) pairs; 1 = always the
@@ -93,6 +94,8 @@ typedef struct tnsb_stats {
     float   cell_size;           /* grid cell edge actually used (>= largest search radius) */
     float   domain_bottom[3];
     float   domain_top[3];
+    int32_t brick_query;         /* 1: the last run used the brick query (half-radius grid), 0: the cell kernel */
+    int64_t n_slow_queries;      /* brick query: queries answered by its warp-cooperative slow path (dense cells, long lists) */
 } tnsb_stats;
 
 /* ---- life cycle --------------------------------------------------------------------------------------------------- */

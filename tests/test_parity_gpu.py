@@ -409,10 +409,11 @@ def test_set_active_search_overloads(tnsb):
     assert eng.does_set_exist(2) and not eng.does_set_exist(3)
 
 
-# ---------------------------------------------------------------------------------------------------- the round kernel (option 1)
-# TNSB_OPT_QUERY_KERNEL = 1: grid sorted by row keys + prefix cell table, a lane owns a query (csrc/query_rounds.cuh).  Same contract.
+# ---------------------------------------------------------------------------------------------------- the cell kernel (option 1)
+# TNSB_OPT_QUERY_KERNEL = 1: cell = r grid sorted by Morton keys, a lane owns a candidate (csrc/query.cuh); the default (0) is the
+# brick query on the half-radius grid (csrc/query_brick.cuh), which falls back to the cell kernel on huge sparse domains.  Same contract.
 @pytest.mark.parametrize("name", list(cases.GOLDEN_CASES))
-def test_round_kernel_golden(tnsb, golden, name):
+def test_cell_kernel_golden(tnsb, golden, name):
     case = cases.GOLDEN_CASES[name]()
     eng = run_engine(tnsb, case, options={tnsb.TNSB_OPT_QUERY_KERNEL: 1})
     for (i, j) in case["pairs"]:
@@ -421,7 +422,7 @@ def test_round_kernel_golden(tnsb, golden, name):
         assert np.array_equal(idx, golden[f"{name}/{i}_{j}/indices"]), (name, i, j)
 
 
-def test_round_kernel_slow_paths_and_limits(tnsb):
+def test_cell_kernel_slow_paths_and_limits(tnsb):
     opt = {tnsb.TNSB_OPT_QUERY_KERNEL: 1}
     # neighbourhoods larger than a tile, lists longer than the private lists and than the staging buffer
     rs = np.random.RandomState(8)
@@ -447,14 +448,14 @@ def test_round_kernel_slow_paths_and_limits(tnsb):
     assert_matches_port(eng, case)
 
 
-def test_round_kernel_c1_and_zsort(tnsb):
+def test_cell_kernel_c1_and_zsort(tnsb):
     n = 100_000
     pts = clouds.uniform_cloud(n, 42).copy()
     r = float(clouds.radius_for_mean_neighbors(n))
     case = dict(sets=[(pts, None)], radius=r, pairs=[(0, 0)], symmetric=True)
     eng = run_engine(tnsb, case, options={tnsb.TNSB_OPT_QUERY_KERNEL: 1})
     assert_matches_port(eng, case)
-    # the order handed to the user is still the libmorton Z-order, although the grid itself is sorted by row keys
+    # the order handed to the user is the libmorton Z-order
     eng.prepare_zsort()
     order = eng.get_zsort_order(0).copy()
     assert np.array_equal(np.sort(order), np.arange(n))

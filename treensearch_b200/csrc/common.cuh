@@ -16,6 +16,13 @@ struct GridParams {
     int    max_coord;   // (1 << bits) - 1
 };
 
+// grid of the brick query (query_brick.cuh): half-radius cells, nx x ny x nz of them, linear row keys (z * ny + y) * nx + x
+struct BrickGrid {
+    double bottom[3];
+    double inv_cell;
+    int nx, ny, nz;
+};
+
 __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -107,63 +114,6 @@ __device__ __forceinline__ Key morton_neighbor(Key key, int ox, int oy, int oz, 
         const Key part = key & md;
         Key r = part;
         if (o[d] > 0) { valid = valid && (part != md); r = ((key | ~md) + (Key)1) & md; }
-        if (o[d] < 0) { valid = valid && (part != 0); r = (part - (Key)1) & md; }
-        out |= r;
-    }
-    return out;
-}
-
-// ---- row keys: key = (interleave(y, z) << bits) | x.  Cells of one (y, z) row are CONSECUTIVE keys, rows follow a 2-D Z curve.
-// Consequence for the query: the 3 x 3 x 3 neighbourhood of a cell is 9 contiguous runs of the sorted point array (one per
-// neighbouring row, three cells long) instead of up to 27 runs under a 3-D Morton order, and "start of cell (row, x)" for ALL
-// cells -- occupied or not -- is one prefix table lookup.  Used by the round query kernel; the Z-order handed to the user by
-// prepare_zsort() is still the libmorton order (Morton<Key>).
-__host__ __device__ __forceinline__ uint32_t dilate2_10(uint32_t v)      // 10 bits -> even bit positions of 20 bits
-{
-    v &= 0x3ffu;
-    v = (v | (v << 8)) & 0x00ff00ffu;
-    v = (v | (v << 4)) & 0x0f0f0f0fu;
-    v = (v | (v << 2)) & 0x33333333u;
-    v = (v | (v << 1)) & 0x55555555u;
-    return v;
-}
-__host__ __device__ __forceinline__ uint64_t dilate2_21(uint64_t v)      // 21 bits -> even bit positions of 42 bits
-{
-    v &= 0x1fffffull;
-    v = (v | (v << 16)) & 0x0000ffff0000ffffull;
-    v = (v | (v << 8)) & 0x00ff00ff00ff00ffull;
-    v = (v | (v << 4)) & 0x0f0f0f0f0f0f0f0full;
-    v = (v | (v << 2)) & 0x3333333333333333ull;
-    v = (v | (v << 1)) & 0x5555555555555555ull;
-    return v;
-}
-template <typename Key> struct RowKey;
-template <> struct RowKey<uint32_t> {
-    static constexpr uint32_t kY = 0x55555555u;
-    __host__ __device__ static __forceinline__ uint32_t encode(uint32_t x, uint32_t y, uint32_t z, int bits)
-    {
-        return ((dilate2_10(y) | (dilate2_10(z) << 1)) << bits) | x;
-    }
-};
-template <> struct RowKey<uint64_t> {
-    static constexpr uint64_t kY = 0x5555555555555555ull;
-    __host__ __device__ static __forceinline__ uint64_t encode(uint32_t x, uint32_t y, uint32_t z, int bits)
-    {
-        return ((dilate2_21(y) | (dilate2_21(z) << 1)) << bits) | (uint64_t)x;
-    }
-};
-// neighbouring row (oy, oz in {-1, 0, 1}) by dilated-integer arithmetic; `valid` is cleared when it leaves the grid
-template <typename Key>
-__device__ __forceinline__ Key row_neighbor(Key row, int oy, int oz, Key row_mask /* (1 << 2*bits) - 1 */, bool& valid)
-{
-    Key out = 0;
-    const int o[2] = { oy, oz };
-#pragma unroll
-    for (int d = 0; d < 2; d++) {
-        const Key md = (RowKey<Key>::kY << d) & row_mask;
-        const Key part = row & md;
-        Key r = part;
-        if (o[d] > 0) { valid = valid && (part != md); r = ((row | ~md) + (Key)1) & md; }
         if (o[d] < 0) { valid = valid && (part != 0); r = (part - (Key)1) & md; }
         out |= r;
     }

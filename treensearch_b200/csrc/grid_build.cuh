@@ -71,9 +71,8 @@ __global__ void __launch_bounds__(kAabbThreads) aabb_kernel(const T* __restrict_
 
 // ----------------------------------------------------------------------------------------------------------------------
 // Cell assignment + Morton key.  ijk = floor((p - bottom) * inv_cell) like TreeNSearch.cpp:713-715, but in fp64 and clamped.
-// row_order = 0: 3-D Morton keys (libmorton order); 1: row keys (x consecutive inside a (y, z) row, common.cuh RowKey).
 template <typename Key>
-__global__ void __launch_bounds__(256) keygen_kernel(const float* __restrict__ pts, int n, int stride, GridParams g, Key* __restrict__ keys, int row_order)
+__global__ void __launch_bounds__(256) keygen_kernel(const float* __restrict__ pts, int n, int stride, GridParams g, Key* __restrict__ keys)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -85,7 +84,7 @@ __global__ void __launch_bounds__(256) keygen_kernel(const float* __restrict__ p
     cx = min(max(cx, 0), g.max_coord);
     cy = min(max(cy, 0), g.max_coord);
     cz = min(max(cz, 0), g.max_coord);
-    keys[i] = row_order ? RowKey<Key>::encode((uint32_t)cx, (uint32_t)cy, (uint32_t)cz, g.bits) : Morton<Key>::encode((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+    keys[i] = Morton<Key>::encode((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
 }
 
 // ----------------------------------------------------------------------------------------------------------------------
@@ -211,7 +210,7 @@ __global__ void __launch_bounds__(256) dense_table_kernel(const Key* __restrict_
 // The order of the points INSIDE a cell is the arrival order of the atomics (not the input order as with the stable radix
 // sort); neighbour SETS do not depend on it.  prepare_zsort() and TNSB_OPT_BUILD = 1 use the radix path.
 template <typename Key>
-__global__ void __launch_bounds__(256) keygen_count_kernel(const float* __restrict__ pts, int n, int stride, GridParams g, Key* __restrict__ keys, int row_order,
+__global__ void __launch_bounds__(256) keygen_count_kernel(const float* __restrict__ pts, int n, int stride, GridParams g, Key* __restrict__ keys,
                                                            uint32_t* __restrict__ population)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -224,7 +223,27 @@ __global__ void __launch_bounds__(256) keygen_count_kernel(const float* __restri
     cx = min(max(cx, 0), g.max_coord);
     cy = min(max(cy, 0), g.max_coord);
     cz = min(max(cz, 0), g.max_coord);
-    const Key k = row_order ? RowKey<Key>::encode((uint32_t)cx, (uint32_t)cy, (uint32_t)cz, g.bits) : Morton<Key>::encode((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+    const Key k = Morton<Key>::encode((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+    keys[i] = k;
+    atomicAdd(population + k, 1u);
+}
+
+// the same pass for the brick query's grid (query_brick.cuh): half-radius cells, linear row keys  key = (z * ny + y) * nx + x.
+// The cell arithmetic must stay identical to brick_cell() in query_brick.cuh (fp64 subtract, multiply, floor, clamp).
+__global__ void __launch_bounds__(256) brick_keygen_count_kernel(const float* __restrict__ pts, int n, int stride, BrickGrid g, uint32_t* __restrict__ keys,
+                                                                 uint32_t* __restrict__ population)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = pts + (int64_t)i * stride;
+    const float x = p[0], y = p[1], z = p[2];
+    int cx = __double2int_rd(((double)x - g.bottom[0]) * g.inv_cell);
+    int cy = __double2int_rd(((double)y - g.bottom[1]) * g.inv_cell);
+    int cz = __double2int_rd(((double)z - g.bottom[2]) * g.inv_cell);
+    cx = min(max(cx, 0), g.nx - 1);
+    cy = min(max(cy, 0), g.ny - 1);
+    cz = min(max(cz, 0), g.nz - 1);
+    const uint32_t k = ((uint32_t)cz * (uint32_t)g.ny + (uint32_t)cy) * (uint32_t)g.nx + (uint32_t)cx;
     keys[i] = k;
     atomicAdd(population + k, 1u);
 }

@@ -60,7 +60,6 @@ struct QueryArgs {
     const float* c_r2;
     const typename HashSlot<Key>::Raw* htable;   // cell key -> [start, end) of the cell's run in c_pts (sparse / huge domains)
     const uint2* dense;           // Morton-indexed direct table {start, end} (domains of <= 2^27 cells): no probing at all
-    const uint32_t* first;        // row-key mode (round kernel): first[key] = points with a smaller key, for every key in [0, 2^(3 bits)]
     int bits;                     // cells per axis = 1 << bits
     int hash_log2;
     int same_set;

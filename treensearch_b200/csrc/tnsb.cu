@@ -11,7 +11,7 @@
 #include "radix_sort.cuh"
 #include "grid_build.cuh"
 #include "query.cuh"
-#include "query_rounds.cuh"
+#include "query_brick.cuh"
 #include "shard.cuh"
 
 #include <algorithm>
@@ -70,6 +70,10 @@ struct PairCounters {
     uint32_t ticket;
     int overflow;
     int minmax[2];
+    // brick query: number of bricks planned, plan buffer overflow, queries that took the slow path
+    uint32_t n_tasks;
+    int plan_overflow;
+    unsigned long long n_slow;
 };
 
 struct SetState {
@@ -98,7 +102,6 @@ struct SetState {
     bool use_dense = false;
     DevBuf first;                  // prefix cell table first[key] for every key in [0, 2^key_bits] (+ scan scratch behind it): bucket build, row-key mode
     DevBuf cursor;                 // bucket build: next free slot of every cell during the scatter
-    bool use_table = false;
     bool bucket = false;           // the last build of this set was a bucket build (no sorted permutation in vals[])
     bool order_valid = false;      // vals[sel] holds the stable sorted permutation of the last build
     int hash_log2 = 1;
@@ -112,6 +115,8 @@ struct SetState {
 
 struct PairState {
     DevBuf d_ragged, d_list_pos;
+    DevBuf d_tasks;            // brick query: the planned bricks
+    int64_t max_tasks = 0;
     PinBuf h_ragged, h_list_pos;
     int64_t capacity = 0;      // ints
     bool in_host = false;      // zero-copy mode: the query kernel wrote the lists straight into h_ragged (mapped pinned memory)
@@ -153,15 +158,18 @@ struct tnsb_context {
     int opt_point_stride = 3;
     int opt_bucket_passes = 0;          // 0: automatic
     int opt_build = 0;             // 0: bucket build when the cell table is small enough, else radix sort; 1: always radix sort
-    int opt_query_kernel = 0;      // 0: query_kernel (candidates in registers, lane = candidate; Morton keys), 1: query_rounds_kernel (lane = query; row keys)
+    int opt_query_kernel = 0;      // 0: automatic (brick query on the half-radius grid while its cell table is affordable, else the cell kernel), 1: always the cell kernel
+    int brick_kmax = 64;           // hit column height of the brick query; raised (sticky) when too many queries overflow it
 
     // world box with hysteresis (TreeNSearch.cpp:474-482)
     bool domain_valid = false;
     double dom_bottom[3] = { 0, 0, 0 }, dom_top[3] = { 0, 0, 0 };
     double cell = 0.0;
+    double r_max = 0.0;            // largest search distance of the last build
     int bits = 0;
     bool key64 = false;
-    bool grid_row_mode = false;    // key order of the grid built last: row keys (round kernel) or 3-D Morton keys (cell kernel, zsort)
+    bool brick_mode = false;       // grid built last: half-radius cells + linear row keys (brick query) or cell = r + 3-D Morton keys (cell kernel, zsort)
+    BrickGrid bgrid;
 
     DevBuf d_reduce;        // 8 x uint32
     DevBuf d_counters;      // PairCounters per pair
@@ -248,16 +256,13 @@ int validate(tnsb_context* c)
 // to the grid).  Keys above encode(ext) cannot occur, so the cell tables only cover [0, encode(ext)]: a flat or elongated cloud
 // (dam-break tank, a Z slab of a sharded cloud) gets a table that matches its extent instead of the cubic power-of-two grid.
 template <typename Key>
-int build_sets(tnsb_context* c, const GridParams& gp, bool row_mode, bool need_order, const int ext[3])
+int build_sets(tnsb_context* c, const GridParams& gp, bool need_order, const int ext[3])
 {
     cudaStream_t s = c->stream;
     int& launches = c->stats.n_kernel_launches;
     const int key_bits = 3 * gp.bits;
     const int n_sets = (int)c->sets.size();
-    const int64_t n_keys = sizeof(Key) == 4
-        ? (int64_t)(row_mode ? RowKey<Key>::encode((uint32_t)ext[0], (uint32_t)ext[1], (uint32_t)ext[2], gp.bits)
-                             : Morton<Key>::encode((uint32_t)ext[0], (uint32_t)ext[1], (uint32_t)ext[2])) + 1
-        : -1;
+    const int64_t n_keys = sizeof(Key) == 4 ? (int64_t)Morton<Key>::encode((uint32_t)ext[0], (uint32_t)ext[1], (uint32_t)ext[2]) + 1 : -1;
     // Per set: bucket build (one counting pass over the full cell key, see grid_build.cuh) while the cell table is small next to the
     // point count, else -- huge sparse domains, 64-bit keys, prepare_zsort (needs the stable permutation), TNSB_OPT_BUILD = 1 -- the LSD
     // radix sort of (key, index) pairs.
@@ -277,9 +282,9 @@ int build_sets(tnsb_context* c, const GridParams& gp, bool row_mode, bool need_o
             TNSB_CUDA(c, st.first.ensure(sizeof(uint32_t) * (size_t)(n_entries + exclusive_scan_temp_elems(n_entries))));
             TNSB_CUDA(c, st.cursor.ensure(sizeof(uint32_t) * (size_t)n_keys));
             TNSB_CUDA(c, cudaMemsetAsync(st.first.p, 0, sizeof(uint32_t) * (size_t)n_entries, s));
-            keygen_count_kernel<Key><<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.n, st.d_stride, gp, st.keys[0].as<Key>(), row_mode ? 1 : 0, st.first.as<uint32_t>());
+            keygen_count_kernel<Key><<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.n, st.d_stride, gp, st.keys[0].as<Key>(), st.first.as<uint32_t>());
         } else {
-            keygen_kernel<Key><<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.n, st.d_stride, gp, st.keys[0].as<Key>(), row_mode ? 1 : 0);
+            keygen_kernel<Key><<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.n, st.d_stride, gp, st.keys[0].as<Key>());
         }
         launches++;
     }
@@ -344,18 +349,13 @@ int build_sets(tnsb_context* c, const GridParams& gp, bool row_mode, bool need_o
         auto& st = c->sets[si];
         st.n_cells = st.n > 0 ? (int)h_ncells[si] : 0;
         c->stats.n_cells += st.n_cells;
-        // neighbour lookup structure.
-        //   row keys (round kernel): prefix table first[key] over ALL cells while that is affordable, else a hash of the occupied cells;
-        //   Morton keys (cell kernel): dense Morton-indexed {start, end} table while the grid has <= 2^27 cells, else the hash
-        //   (open addressing at <= 33% load, 16-byte slots {key, start, end}).
-        st.use_table = row_mode && (st.bucket || (n_keys > 0 && n_keys <= (1ll << 26) && n_keys <= std::max<int64_t>(1ll << 22, 8ll * st.n)));
-        st.use_dense = !row_mode && (st.bucket || key_bits <= 27);
-        if (st.use_table && !st.bucket) {
-            const int64_t n_entries = n_keys + 1;
-            TNSB_CUDA(c, st.first.ensure(sizeof(uint32_t) * (size_t)(n_entries + exclusive_scan_temp_elems(n_entries))));
-            TNSB_CUDA(c, cudaMemsetAsync(st.first.p, 0, sizeof(uint32_t) * (size_t)n_entries, s));
-        } else if (st.use_dense) {
-            const size_t dbytes = st.bucket ? sizeof(uint2) * (size_t)n_keys : sizeof(uint2) << key_bits;      // bucket build: every entry of [0, n_keys) is rewritten
+        // neighbour lookup structure of the cell kernel: dense Morton-indexed {start, end} table while it is small next to the
+        // occupied cells (always after a bucket build, whose prefix table has the same extent), else an open addressing hash
+        // of the occupied cells (<= 33% load, 16-byte slots {key, start, end}).  Empty sets get a 2-slot all-empty hash.
+        const size_t dense_bytes = st.bucket ? sizeof(uint2) * (size_t)n_keys : (key_bits <= 27 ? sizeof(uint2) << key_bits : ~(size_t)0);
+        st.use_dense = st.n > 0 && (st.bucket || (key_bits <= 27 && dense_bytes <= std::max<size_t>((size_t)64 << 20, (size_t)512 * (size_t)st.n_cells)));
+        if (st.use_dense) {
+            const size_t dbytes = dense_bytes;      // bucket build: every entry of [0, n_keys) is rewritten
             const bool fresh = st.dense.cap < dbytes || st.dense_bits != key_bits;
             TNSB_CUDA(c, st.dense.ensure(dbytes));
             if (st.bucket) {
@@ -370,7 +370,7 @@ int build_sets(tnsb_context* c, const GridParams& gp, bool row_mode, bool need_o
             }
             st.dense_bits = key_bits;
             st.dense_cells = 0;
-        } else if (!st.use_table) {
+        } else {
             int lg = 1;
             while ((1ll << lg) < 3ll * st.n_cells) lg++;
             st.hash_log2 = lg;
@@ -394,12 +394,7 @@ int build_sets(tnsb_context* c, const GridParams& gp, bool row_mode, bool need_o
             emit_cells_kernel<Key><<<n_tiles, kCellThreads, 0, s>>>(st.keys[st.sel].as<Key>(), st.n, st.tile_heads.as<uint32_t>(), st.cell_key.as<Key>(),
                                                                   st.cell_start.as<uint32_t>());
             launches += 2;                   // emit_cells + the table / hash kernel below
-            if (st.use_table) {
-                const int64_t n_entries = n_keys + 1;
-                uint32_t* first = st.first.as<uint32_t>();
-                cell_population_kernel<Key><<<ceil_div(st.n_cells, 256), 256, 0, s>>>(st.cell_key.as<Key>(), st.cell_start.as<uint32_t>(), st.n_cells, first);
-                launches += exclusive_scan_u32(first, first, n_entries, first + n_entries, nullptr, s);
-            } else if (st.use_dense) {
+            if (st.use_dense) {
                 dense_table_kernel<Key><<<ceil_div(st.n_cells, 256), 256, 0, s>>>(st.cell_key.as<Key>(), st.cell_start.as<uint32_t>(), st.n_cells,
                                                                                  st.dense.as<uint2>(), 1);
                 st.dense_cells = st.n_cells;
@@ -432,21 +427,6 @@ cudaError_t launch_query(const QueryArgs<Key>& a, bool variable, bool symmetric,
     return go(query_kernel<Key, NSLOT, true, true, DENSE>);
 }
 
-template <typename Key, int NT, bool DENSE>
-cudaError_t launch_query_rounds(const QueryArgs<Key>& a, bool variable, bool symmetric, int n_sms, cudaStream_t s)
-{
-    // persistent CTAs, one per SM: every warp owns ~23 KB of shared memory (tiles + private hit lists)
-    auto go = [&](auto kernel, int smem, int threads) -> cudaError_t {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        kernel<<<n_sms, threads, smem, s>>>(a);
-        return cudaGetLastError();
-    };
-    if (!variable) return go(query_rounds_kernel<Key, NT, false, false, DENSE>, RLayout<NT, false>::kBytes, RLayout<NT, false>::kThreads);
-    if (!symmetric) return go(query_rounds_kernel<Key, NT, true, false, DENSE>, RLayout<NT, false>::kBytes, RLayout<NT, false>::kThreads);
-    return go(query_rounds_kernel<Key, NT, true, true, DENSE>, RLayout<NT, true>::kBytes, RLayout<NT, true>::kThreads);
-}
-
 template <typename Key>
 int query_pair(tnsb_context* c, int si, int sj, const GridParams& gp, PairCounters* d_cnt)
 {
@@ -464,7 +444,6 @@ int query_pair(tnsb_context* c, int si, int sj, const GridParams& gp, PairCounte
     a.c_r2 = cj.sorted_r2.as<float>();
     a.htable = cj.htable.as<typename HashSlot<Key>::Raw>();
     a.dense = cj.dense.as<uint2>();
-    a.first = cj.first.as<uint32_t>();
     a.bits = gp.bits;
     a.hash_log2 = cj.hash_log2;
     a.same_set = si == sj;
@@ -484,14 +463,140 @@ int query_pair(tnsb_context* c, int si, int sj, const GridParams& gp, PairCounte
     const int grid = c->n_sms;
     cudaError_t e;
     const bool small = 27.0 * avg_cell * 1.15 <= 256.0;
-    if (c->grid_row_mode) {
-        // tiles of 256 candidates (4 cells per round) for the usual SPH densities, 512 (2 cells per round) for dense clouds
-        if (cj.use_table) e = small ? launch_query_rounds<Key, 4, true>(a, variable, symmetric, grid, c->stream) : launch_query_rounds<Key, 2, true>(a, variable, symmetric, grid, c->stream);
-        else e = small ? launch_query_rounds<Key, 4, false>(a, variable, symmetric, grid, c->stream) : launch_query_rounds<Key, 2, false>(a, variable, symmetric, grid, c->stream);
-    } else if (cj.use_dense) e = small ? launch_query<Key, 8, true>(a, variable, symmetric, grid, c->stream) : launch_query<Key, 16, true>(a, variable, symmetric, grid, c->stream);
+    if (cj.use_dense) e = small ? launch_query<Key, 8, true>(a, variable, symmetric, grid, c->stream) : launch_query<Key, 16, true>(a, variable, symmetric, grid, c->stream);
     else e = small ? launch_query<Key, 8, false>(a, variable, symmetric, grid, c->stream) : launch_query<Key, 16, false>(a, variable, symmetric, grid, c->stream);
     TNSB_CUDA(c, e);
     c->stats.n_kernel_launches++;
+    c->stats.n_query_launches++;
+    return TNSB_OK;
+}
+
+// ---- brick query path (query_brick.cuh): half-radius grid, linear row keys, prefix cell table first[] per set -------------------
+// Sorted grid of every set by the bucket build: cell populations (L2 atomics) -> exclusive scan -> scatter of the records.
+int build_sets_brick(tnsb_context* c, const BrickGrid& bg)
+{
+    cudaStream_t s = c->stream;
+    int& launches = c->stats.n_kernel_launches;
+    const int64_t n_keys = (int64_t)bg.nx * bg.ny * bg.nz;
+    const int64_t n_entries = n_keys + 1;
+    for (auto& st : c->sets) {
+        st.bucket = true;
+        st.order_valid = false;
+        st.n_cells = 0;
+        // every set -- empty ones too -- gets a prefix table: the planner and the slab staging read it for any searched set
+        TNSB_CUDA(c, st.first.ensure(sizeof(uint32_t) * (size_t)(n_entries + exclusive_scan_temp_elems(n_entries))));
+        TNSB_CUDA(c, cudaMemsetAsync(st.first.p, 0, sizeof(uint32_t) * (size_t)n_entries, s));
+        if (st.n == 0) continue;
+        TNSB_CUDA(c, st.keys[0].ensure(sizeof(uint32_t) * (size_t)st.n, 1.1));
+        TNSB_CUDA(c, st.cursor.ensure(sizeof(uint32_t) * (size_t)n_keys));
+        brick_keygen_count_kernel<<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.n, st.d_stride, bg, st.keys[0].as<uint32_t>(), st.first.as<uint32_t>());
+        launches++;
+    }
+    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_KEYS], s));
+    for (auto& st : c->sets) {
+        if (st.n == 0) continue;
+        uint32_t* first = st.first.as<uint32_t>();
+        launches += exclusive_scan_u32(first, first, n_entries, first + n_entries, nullptr, s);
+        TNSB_CUDA(c, cudaMemcpyAsync(st.cursor.p, first, sizeof(uint32_t) * (size_t)n_keys, cudaMemcpyDeviceToDevice, s));
+        c->stats.sort_passes = std::max(c->stats.sort_passes, 1);
+    }
+    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_SORT], s));
+    for (auto& st : c->sets) {
+        if (st.n == 0) continue;
+        TNSB_CUDA(c, st.sorted.ensure(sizeof(float4) * (size_t)st.n, 1.1));
+        if (st.has_radii) TNSB_CUDA(c, st.sorted_r2.ensure(sizeof(float) * (size_t)st.n, 1.1));
+        const int passes = c->opt_bucket_passes > 0 ? c->opt_bucket_passes : (int)std::min<int64_t>(16, std::max<int64_t>(1, ((int64_t)st.n * 16 + (80ll << 20) - 1) / (80ll << 20)));
+        for (int p = 0; p < passes; p++) {
+            const uint32_t lo = (uint32_t)(n_keys * p / passes), hi = (uint32_t)(n_keys * (p + 1) / passes);
+            bucket_scatter_kernel<uint32_t><<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.d_stride, st.has_radii ? st.d_radii : nullptr, st.keys[0].as<uint32_t>(), st.n,
+                                                                              st.cursor.as<uint32_t>(), st.sorted.as<float4>(), st.sorted_r2.as<float>(), lo, hi);
+        }
+        launches += passes;
+        st.sorted_valid = true;
+    }
+    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_REORDER], s));
+    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_CELLS], s));
+    TNSB_CUDA(c, cudaGetLastError());
+    return TNSB_OK;
+}
+
+// shared memory geometry of the brick query: records per slab and hits per lane column, chosen so that two CTAs of 8 warps
+// (kmax = 64) or one CTA of 12 warps (kmax = 128, dense clouds) fit an SM
+struct BrickConfig { int slab_cap, kmax, n_warps, blocks_per_sm; };
+BrickConfig brick_config(bool symmetric, int kmax)
+{
+    BrickConfig b;
+    b.kmax = kmax <= 64 ? 64 : 128;
+    if (b.kmax == 64) { b.n_warps = 8; b.blocks_per_sm = 2; b.slab_cap = symmetric ? 1792 : 2304; }
+    else { b.n_warps = 12; b.blocks_per_sm = 1; b.slab_cap = symmetric ? 2560 : 3072; }
+    return b;
+}
+
+int query_pair_brick(tnsb_context* c, int si, int sj, PairCounters* d_cnt)
+{
+    auto& qi = c->sets[si];
+    auto& cj = c->sets[sj];
+    PairState& ps = c->pairs[si * c->sets.size() + sj];
+    const bool variable = !c->radius_set;
+    const bool symmetric = variable && c->symmetric;   // TreeNSearch.cpp:2431
+    const BrickConfig bc = brick_config(symmetric, c->brick_kmax);
+    const BrickGrid& bg = c->bgrid;
+    BrickArgs a;
+    a.g = bg;
+    a.q_pts = qi.sorted.as<float4>();
+    a.q_r2 = qi.sorted_r2.as<float>();
+    a.q_first = qi.first.as<uint32_t>();
+    a.c_pts = cj.sorted.as<float4>();
+    a.c_r2 = cj.sorted_r2.as<float>();
+    a.c_first = cj.first.as<uint32_t>();
+    a.same_set = si == sj;
+    a.query_limit = c->opt_query_limit >= 0 ? (int)std::min<int64_t>(c->opt_query_limit, INT_MAX) : INT_MAX;
+    a.r2_fixed = c->radius_sq;
+    // rows / cells farther than the largest search distance (in cells, 0.2 % slack over the float rounding of the test) are culled
+    const double rc = c->r_max * bg.inv_cell;
+    a.cull_r2 = (float)(rc * rc * 1.002);
+    a.inv_cell_f = (float)bg.inv_cell;
+    const int64_t n_bricks = (int64_t)ceil_div(bg.nx, kBX) * ceil_div(bg.ny, kBY) * ceil_div(bg.nz, kBZ);
+    const int64_t want_tasks = std::max<int64_t>(ps.max_tasks, n_bricks + n_bricks / 2 + 1024);
+    TNSB_CUDA(c, ps.d_tasks.ensure(sizeof(BrickTask) * (size_t)want_tasks));
+    ps.max_tasks = (int64_t)(ps.d_tasks.cap / sizeof(BrickTask));
+    a.tasks = ps.d_tasks.as<BrickTask>();
+    a.max_tasks = (uint32_t)std::min<int64_t>(ps.max_tasks, 0x7fffffff);
+    a.n_tasks = &d_cnt->n_tasks;
+    a.plan_overflow = &d_cnt->plan_overflow;
+    a.ticket = &d_cnt->ticket;
+    a.slab_cap = bc.slab_cap;
+    a.kmax = bc.kmax;
+    a.ragged = ps.in_host ? ps.h_ragged.as<int32_t>() : ps.d_ragged.as<int32_t>();
+    a.capacity = ps.capacity;
+    a.list_pos = ps.d_list_pos.as<long long>();
+    a.cursor = &d_cnt->cursor;
+    a.n_neighbors = &d_cnt->n_neighbors;
+    a.n_slow = &d_cnt->n_slow;
+    a.overflow = &d_cnt->overflow;
+    cudaStream_t s = c->stream;
+    brick_plan_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(n_bricks, 8), 8 * c->n_sms), 256, 0, s>>>(bg, a.q_first, a.c_first, a.slab_cap, a.tasks, a.max_tasks, a.n_tasks, a.plan_overflow);
+    TNSB_CUDA(c, cudaGetLastError());
+    const int smem = brick_layout(bc.slab_cap, bc.kmax, bc.n_warps, symmetric).total;
+    const int grid = c->n_sms * bc.blocks_per_sm;
+    auto go = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        kernel<<<grid, bc.n_warps * 32, smem, s>>>(a);
+        return cudaGetLastError();
+    };
+    cudaError_t e;
+    if (bc.kmax == 64) {
+        if (!variable) e = go(brick_query_kernel<8, 2, false, false>);
+        else if (!symmetric) e = go(brick_query_kernel<8, 2, true, false>);
+        else e = go(brick_query_kernel<8, 2, true, true>);
+    } else {
+        if (!variable) e = go(brick_query_kernel<12, 1, false, false>);
+        else if (!symmetric) e = go(brick_query_kernel<12, 1, true, false>);
+        else e = go(brick_query_kernel<12, 1, true, true>);
+    }
+    TNSB_CUDA(c, e);
+    c->stats.n_kernel_launches += 2;
     c->stats.n_query_launches++;
     return TNSB_OK;
 }
@@ -502,7 +607,7 @@ double ms_since(const std::chrono::steady_clock::time_point& t0)
 }
 
 // upload + world box + grid parameters + sorted grid of every set.  Shared by run() and prepare_zsort().
-int build_grid(tnsb_context* c, GridParams* gp_out, bool row_mode, bool need_order)
+int build_grid(tnsb_context* c, GridParams* gp_out, bool want_brick, bool need_order)
 {
     cudaStream_t s = c->stream;
     const int n_sets = (int)c->sets.size();
@@ -609,8 +714,31 @@ int build_grid(tnsb_context* c, GridParams* gp_out, bool row_mode, bool need_ord
         const double mc = std::floor(((double)hi[d] - gp.bottom[d]) * gp.inv_cell);
         ext[d] = (int)std::min<double>((double)gp.max_coord, std::max(0.0, mc) + 2.0);
     }
-    c->grid_row_mode = row_mode;
-    return c->key64 ? build_sets<uint64_t>(c, gp, row_mode, need_order, ext) : build_sets<uint32_t>(c, gp, row_mode, need_order, ext);
+    c->r_max = r_max;
+    // ---- brick query grid: half-radius cells over the occupied extent, linear row keys.  Taken while its prefix table (one
+    // uint32 per cell and per set) is small next to the point count; huge sparse domains keep the cell kernel + hash.
+    c->brick_mode = false;
+    if (want_brick && !need_order) {
+        BrickGrid bg;
+        int64_t dims[3];
+        bg.inv_cell = 2.0 / c->cell;
+        for (int d = 0; d < 3; d++) {
+            bg.bottom[d] = c->dom_bottom[d];
+            dims[d] = (int64_t)std::floor(((double)hi[d] - bg.bottom[d]) * bg.inv_cell) + 1;
+        }
+        int64_t n_max = 0;
+        for (auto& st : c->sets) n_max = std::max<int64_t>(n_max, st.n);
+        const double n_keys_f = (double)dims[0] * (double)dims[1] * (double)dims[2];
+        if (dims[0] >= 1 && dims[1] >= 1 && dims[2] >= 1 && n_keys_f <= (double)(1ll << 30) && n_keys_f <= (double)std::max<int64_t>(1ll << 22, 8 * n_max)) {
+            bg.nx = (int)dims[0]; bg.ny = (int)dims[1]; bg.nz = (int)dims[2];
+            c->bgrid = bg;
+            c->brick_mode = true;
+            c->stats.cell_size = (float)(0.5 * c->cell);
+            c->stats.brick_query = 1;
+            return build_sets_brick(c, bg);
+        }
+    }
+    return c->key64 ? build_sets<uint64_t>(c, gp, need_order, ext) : build_sets<uint32_t>(c, gp, need_order, ext);
 }
 
 float ev_ms(tnsb_context* c, int a, int b)
@@ -639,7 +767,7 @@ int run_impl(tnsb_context* c)
     GridParams gp;
     memset(&gp, 0, sizeof(gp));
     if (n_total > 0) {
-        rc = build_grid(c, &gp, c->opt_query_kernel == 1, false);
+        rc = build_grid(c, &gp, c->opt_query_kernel == 0, false);
         if (rc != TNSB_OK) return rc;
     } else {
         for (int k = 0; k < EV_COUNT; k++) TNSB_CUDA(c, cudaEventRecord(c->ev[k], s));
@@ -690,8 +818,9 @@ int run_impl(tnsb_context* c)
             TNSB_CUDA(c, cudaMemcpyAsync(c->d_counters.as<PairCounters>() + id, h_init + id, sizeof(PairCounters), cudaMemcpyHostToDevice, s));
         for (int id : todo) {
             const int si = id / n_sets, sj = id % n_sets;
-            rc = c->key64 ? query_pair<uint64_t>(c, si, sj, gp, c->d_counters.as<PairCounters>() + id)
-                          : query_pair<uint32_t>(c, si, sj, gp, c->d_counters.as<PairCounters>() + id);
+            if (c->brick_mode) rc = query_pair_brick(c, si, sj, c->d_counters.as<PairCounters>() + id);
+            else rc = c->key64 ? query_pair<uint64_t>(c, si, sj, gp, c->d_counters.as<PairCounters>() + id)
+                               : query_pair<uint32_t>(c, si, sj, gp, c->d_counters.as<PairCounters>() + id);
             if (rc != TNSB_OK) return rc;
         }
         TNSB_CUDA(c, cudaMemcpyAsync(h_out, c->d_counters.p, sizeof(PairCounters) * n_pairs, cudaMemcpyDeviceToHost, s));
@@ -700,7 +829,13 @@ int run_impl(tnsb_context* c)
         for (int id : todo) {
             PairState& ps = c->pairs[id];
             const PairCounters& r = h_out[id];
-            if (r.overflow) {
+            c->stats.n_slow_queries += (int64_t)r.n_slow;
+            if (r.plan_overflow) {
+                // the planner kept counting: n_tasks is the exact number of bricks
+                ps.max_tasks = (int64_t)r.n_tasks + 1024;
+                again.push_back(id);
+                c->stats.n_reruns++;
+            } else if (r.overflow) {
                 // the cursor kept counting: it is the exact size needed
                 const size_t need = (size_t)((double)r.cursor * 1.1) + 4096;
                 if (ps.in_host) {
@@ -720,6 +855,8 @@ int run_impl(tnsb_context* c)
         }
         todo.swap(again);
     }
+    // lists longer than the brick query's hit columns went through its slow path: use the tall columns from the next run on
+    if (c->brick_mode && c->brick_kmax == 64 && c->stats.n_slow_queries * 50 > std::max<int64_t>(n_total, 1)) c->brick_kmax = 128;
     if (c->opt_sort_lists) {
         for (int id : act) {
             PairState& ps = c->pairs[id];
@@ -842,7 +979,7 @@ void tnsb_destroy(tnsb_context* c)
         st.sorted.release(); st.sorted_r2.release(); st.cell_key.release(); st.cell_start.release(); st.tile_heads.release();
         st.htable.release(); st.dense.release(); st.first.release(); st.cursor.release(); st.d_zorder.release();
     }
-    for (auto& p : c->pairs) { p.d_ragged.release(); p.d_list_pos.release(); p.h_ragged.release(); p.h_list_pos.release(); }
+    for (auto& p : c->pairs) { p.d_ragged.release(); p.d_list_pos.release(); p.d_tasks.release(); p.h_ragged.release(); p.h_list_pos.release(); }
     for (int p = 0; p < 2; p++) {
         for (int r = 0; r < (int)c->win_peer[p].size(); r++)
             if (r != c->win_rank && c->win_peer[p][r]) cudaIpcCloseMemHandle(c->win_peer[p][r]);
@@ -990,7 +1127,7 @@ int tnsb_set_option(tnsb_context* c, int option, int64_t value)
         if (value != 0 && value != 1) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: build must be 0 (automatic) or 1 (radix sort).");
         c->opt_build = (int)value; return TNSB_OK;
     case TNSB_OPT_QUERY_KERNEL:
-        if (value != 0 && value != 1) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: query kernel must be 0 (cell kernel) or 1 (round kernel).");
+        if (value != 0 && value != 1) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: query kernel must be 0 (automatic: brick query) or 1 (cell kernel).");
         c->opt_query_kernel = (int)value; return TNSB_OK;
     case TNSB_OPT_POINT_STRIDE:
         if (value != 3 && value != 4) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: point stride must be 3 (xyz) or 4 (xyz + id).");
@@ -1073,7 +1210,7 @@ int tnsb_prepare_zsort(tnsb_context* c)
     bool all_valid = true;
     int64_t n_total = 0;
     for (auto& st : c->sets) { all_valid = all_valid && ((st.sorted_valid && st.order_valid) || st.n == 0); n_total += st.n; }
-    if ((!all_valid || c->grid_row_mode) && n_total > 0) {
+    if ((!all_valid || c->brick_mode) && n_total > 0) {
         // no grid of the current points yet (TreeNSearch.cpp:2592-2595), or a grid without a stable Morton permutation (bucket build,
         // row-key order): the order handed to the user is the libmorton Z-order, stable inside a cell, so radix sort by Morton keys now
         GridParams gp;
