@@ -3,26 +3,28 @@
 // (TreeNSearch.cpp:1823-1872, :2161-2399, :2400-2569).
 //
 // Grid: cell edge = r_max * (1 + 2^-13) / 2, linear row keys  key = (z * ny + y) * nx + x  (x fastest), prefix table
-// first[key] = number of points with a smaller key (built by the bucket build, grid_build.cuh).  A neighbour of a point of cell
-// (cx, cy, cz) lies in cells [cx-2, cx+2] x [cy-2, cy+2] x [cz-2, cz+2]: 25 rows, and inside a row the cells are CONSECUTIVE keys,
-// i.e. one contiguous run of the sorted point array.  15.6 r^3 of candidate volume instead of the 27 r^3 of a cell = r grid, and
-// per query the rows (and the x extent inside every row) that cannot hold a point within r are culled: ~75 distance tests per
-// query at ~30 neighbours (2.5 tests per hit; the 27-cell stencil needs 6.5).
+// first[key] = number of points with a smaller key, sorted points as PLANES x[], y[], z[], id[] (grid_build.cuh).  A neighbour
+// of a point of cell (cx, cy, cz) lies in cells [cx-2, cx+2] x [cy-2, cy+2] x [cz-2, cz+2]: 25 rows, and inside a row the cells
+// are CONSECUTIVE keys, i.e. one contiguous run of every plane.  15.6 r^3 of candidate volume instead of the 27 r^3 of a
+// cell = r grid, and per query the rows -- and the cells inside every row -- that cannot hold a point within r are culled:
+// ~75 distance tests per query at ~30 neighbours (2.5 tests per hit; the 27-cell stencil needs 6.5).
 //
 // Work decomposition (one launch per active ordered pair set_i -> set_j):
 //   * brick_plan_kernel cuts the grid into bricks of <= 32 x 4 x 4 cells whose candidate SLAB (the brick plus 2 cells on every
-//     side: <= 64 rows of <= 36 cells) fits the shared memory slab buffer; bricks that do not fit are split.
-//   * brick_query_kernel: persistent CTAs pull bricks from a ticket counter.  Per brick one warp reads the row boundaries from
-//     the prefix table and stages every slab row with ONE cp.async.bulk (global -> shared, mbarrier complete_tx) -- the rows
-//     are contiguous 16-byte records (x, y, z, bits(id)); the CTA builds the brick's cell boundary table T (slab position of
-//     every cell boundary) in shared memory meanwhile.
-//   * a warp takes 32 consecutive queries of the brick; every LANE owns one query: it culls its 25 rows, turns them into <= 26
-//     (first, last) slab ranges (its own record is cut out of its own row), and then walks ALL its ranges in one flattened loop:
-//     one LDS.128 per candidate, the reference's exact arithmetic d2 = fma(dz,dz, fma(dx,dx, dy*dy)) <= r^2
-//     (TreeNSearch.cpp:2477-2486 as compiled), a hit is ONE predicated 16-bit store into the lane's private
-//     column.  No ballot, no popc, no shuffle in the inner loop; lanes that run out of candidates early walk a dummy range.
-//   * the warp then reserves room for its 32 lists with one atomicAdd and writes them as [n, j0, j1, ...] (TreeNSearch.h:395),
-//     one coalesced store per 32 list words.
+//     side: <= 64 rows of <= 36 cells) fits a shared memory slab buffer; bricks that do not fit are split.
+//   * brick_query_kernel: one persistent CTA per SM = NCONS consumer warps + 1 producer warp, two slab buffers.
+//     PRODUCER: pulls the next brick from a ticket counter, reads the row boundaries from the prefix table, stages every slab
+//       row with one cp.async.bulk per plane (global -> shared through the TMA unit, completion counted in bytes on the buffer's
+//       `full` mbarrier) and builds the brick's boundary table T (slab position of every cell boundary) -- while the consumers
+//       still work on the previous brick in the other buffer.
+//     CONSUMERS: a warp takes 32 consecutive queries of the brick; every LANE owns one query: it culls its 25 rows, turns them
+//       into <= 26 (first, last) slab ranges (its own record is cut out of its own row), and walks ALL its ranges in one
+//       flattened loop: three conflict-light LDS.32 per candidate (adjacent lanes read adjacent words of a plane), the
+//       reference's exact arithmetic d2 = fma(dz,dz, fma(dx,dx, dy*dy)) <= r^2 (TreeNSearch.cpp:2477-2486 as compiled,
+//       SURVEY.md §0.5), a hit is ONE predicated 16-bit store into the lane's private column.  No ballot, no popc, no shuffle
+//       in the inner loop; lanes that run out of candidates early walk dummy records.  The warp then reserves room for its 32
+//       lists with one atomicAdd and writes them as [n, j0, j1, ...] (TreeNSearch.h:395), one coalesced store per 32 words.
+//       Warps move on to the next brick on their own (`empty` mbarrier per buffer): no CTA-wide barrier anywhere.
 // Queries with more than kMaxTot candidates, lists longer than the column, and cells too dense for any slab take a
 // warp-cooperative two-pass slow path that reads the candidates from global memory.
 #pragma once
@@ -32,10 +34,11 @@
 namespace tnsb {
 
 constexpr int kBX = 32, kBY = 4, kBZ = 4;                // largest brick, in cells
+constexpr int kRowPitch = kBY + 4;                       // slab rows are indexed (z - z0 + 2) * 8 + (y - y0 + 2)
 constexpr int kSlabRows = (kBY + 4) * (kBZ + 4);         // 64 candidate rows per brick
-constexpr int kQRows = kBY * kBZ;                        // 16 query rows per brick
+constexpr int kQRows = kBY * kBZ;                        // 16 query rows per brick, indexed (z - z0) * 4 + (y - y0)
 constexpr int kTW = kBX + 5;                             // cell boundaries per slab row (odd: spreads the rows over the banks)
-constexpr int kDummy = 256;                              // dummy records (x = 3e38) behind the slab
+constexpr int kDummy = 256;                              // dummy records (x = 3e38) behind the x plane
 constexpr int kTabH = 30;                                // per-lane range table: 26 ranges + 2 dummy ranges + landing entry + prefetch
 constexpr int kMaxTot = 512;                             // candidates per query on the fast path
 constexpr int kColStride = 68;                           // bytes between consecutive hits of one lane (34 uint16: conflict-free column reads)
@@ -46,47 +49,21 @@ struct BrickTask {
     uint32_t dims;      // ex | ey << 8 | ez << 16 | flags
 };
 
-struct BrickLayout {
-    int off_slab, off_r2, off_T, off_rowkey, off_g0, off_rowoff, off_qs, off_qoff, off_qdelta, off_qrow, off_misc, off_warp;
-    int tab_bytes, warp_bytes, total;
+// sorted points of one set: records (x, y, z, bits(id)), r^2 (variable radius only), prefix cell table
+struct BrickSet {
+    const float4* pts;
+    const float* r2;
+    const uint32_t* first;
 };
-
-__host__ __device__ inline BrickLayout brick_layout(int slab_cap, int kmax, int n_warps, bool symmetric)
-{
-    BrickLayout L;
-    int o = 0;
-    L.off_slab = o;   o += (slab_cap + kDummy) * 16;                         // slab records, then the dummy records
-    L.off_r2 = o;     o += symmetric ? (slab_cap + kDummy) * 4 : 0;          // candidate r^2 (symmetric variable radius only)
-    L.off_T = o;      o += ((kSlabRows * kTW * 2 + 15) & ~15);
-    L.off_rowkey = o; o += kSlabRows * 4;
-    L.off_g0 = o;     o += kSlabRows * 4;
-    L.off_rowoff = o; o += (kSlabRows + 4) * 4;
-    L.off_qs = o;     o += kQRows * 4;
-    L.off_qoff = o;   o += (kQRows + 4) * 4;
-    L.off_qdelta = o; o += kQRows * 4;
-    L.off_qrow = o;   o += kQRows * 4;
-    L.off_misc = o;   o += 64;
-    L.off_warp = o;
-    L.tab_bytes = kTabH * 32 * 4;
-    L.warp_bytes = (L.tab_bytes + (kmax + 1) * kColStride + 15) & ~15;
-    L.total = o + n_warps * L.warp_bytes;
-    return L;
-}
 
 struct BrickArgs {
     BrickGrid g;
-    // searching set (set_i)
-    const float4* q_pts;
-    const float* q_r2;
-    const uint32_t* q_first;
-    // searched set (set_j)
-    const float4* c_pts;
-    const float* c_r2;
-    const uint32_t* c_first;
+    BrickSet q;               // searching set (set_i)
+    BrickSet c;               // searched set (set_j)
     int same_set;
     int query_limit;
     float r2_fixed;
-    float cull_r2;            // (largest search distance / cell)^2 with 0.1 % slack: rows farther than that are skipped
+    float cull_r2;            // (largest search distance / cell)^2 with 0.2 % slack: rows / cells farther than that are skipped
     float inv_cell_f;
     // plan
     BrickTask* tasks;
@@ -94,8 +71,6 @@ struct BrickArgs {
     uint32_t* n_tasks;
     int* plan_overflow;
     uint32_t* ticket;
-    int slab_cap;             // records
-    int kmax;                 // hits per lane column
     // output
     int32_t* ragged;
     long long capacity;
@@ -104,6 +79,28 @@ struct BrickArgs {
     unsigned long long* n_neighbors;
     unsigned long long* n_slow;
     int* overflow;
+};
+
+// ---- shared memory geometry (bytes) ---------------------------------------------------------------------------------------
+// Per slab buffer: SLAB records + kDummy dummy records (x = 3e38: d2 = inf, never a hit) (+ r^2 of both), boundary table T, meta.
+template <int SLAB, int KMAX, bool SYM>
+struct BrickSmem {
+    static constexpr int kOffSlab = 0;
+    static constexpr int kOffR2 = (SLAB + kDummy) * 16;
+    static constexpr int kOffT = kOffR2 + (SYM ? (SLAB + kDummy) * 4 : 0);
+    static constexpr int kOffMeta = kOffT + ((kSlabRows * kTW * 2 + 15) & ~15);
+    // meta words: [0] x0 [1] y0 [2] z0 [3] dims | flags [4] n queries [5] staged [6] next warp task [7] end
+    //             [8, 24) qs   [24, 41) qoff   [44, 60) qdelta
+    static constexpr int kMetaWords = 64;
+    static constexpr int kOffRowKey = kOffMeta + kMetaWords * 4;        // producer scratch: key of the first cell of every slab row
+    static constexpr int kOffRowBase = kOffRowKey + kSlabRows * 4;      //                   slab position - global position of the row's records
+    static constexpr int kBufBytes = kOffRowBase + kSlabRows * 4;
+    static constexpr int kOffBars = 2 * kBufBytes;                      // full[0], full[1], empty[0], empty[1]
+    static constexpr int kOffWarp = kOffBars + 64;
+    static constexpr int kTabBytes = kTabH * 128;
+    static constexpr int kWarpBytes = (kTabBytes + (KMAX + 1) * kColStride + 15) & ~15;
+    static constexpr int total(int n_cons) { return kOffWarp + n_cons * kWarpBytes; }
+    static_assert((SLAB + kDummy) * 16 < 65536, "slab offsets are stored as 16-bit byte offsets");
 };
 
 // ---- shared memory / mbarrier / bulk copy primitives (32-bit shared window addresses) ---------------------------------------
@@ -138,14 +135,12 @@ __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v)
 }
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
@@ -177,9 +172,8 @@ __device__ __forceinline__ int brick_cell(float v, double bottom, double inv_cel
 // ---------------------------------------------------------------------------------------------------------------------------
 // Plan: one warp per 32 x 4 x 4 brick; bricks without queries are dropped, bricks whose candidate slab exceeds slab_cap are
 // split (x first: rows stay long) down to single cells, which are flagged for the slow path.
-__device__ __forceinline__ uint32_t plan_row_sum(const uint32_t* first, const BrickGrid& g, int xa, int xb, int y0, int ny_rows, int z0, int nz_rows, int lane)
+__device__ __forceinline__ uint32_t plan_rows(const uint32_t* first, const BrickGrid& g, int xa, int xb, int y0, int ny_rows, int z0, int nz_rows, int lane)
 {
-    // sum over rows (y0 .. y0+ny_rows-1) x (z0 .. z0+nz_rows-1), clipped to the grid, of first[row + xb] - first[row + xa]
     uint32_t s = 0;
     const int n_rows = ny_rows * nz_rows;
     for (int r = lane; r < n_rows; r += 32) {
@@ -201,20 +195,19 @@ __global__ void __launch_bounds__(256) brick_plan_kernel(const BrickGrid g, cons
     int(*stack)[6] = s_stack[warp];
     for (long long b = (long long)blockIdx.x * 8 + warp; b < n_bricks; b += (long long)gridDim.x * 8) {
         const int bx = (int)(b % nbx), by = (int)((b / nbx) % nby), bz = (int)(b / ((long long)nbx * nby));
-        int sp = 0;
         if (lane == 0) {
             stack[0][0] = bx * kBX; stack[0][1] = by * kBY; stack[0][2] = bz * kBZ;
             stack[0][3] = min(kBX, g.nx - bx * kBX); stack[0][4] = min(kBY, g.ny - by * kBY); stack[0][5] = min(kBZ, g.nz - bz * kBZ);
         }
-        sp = 1;
+        int sp = 1;
         __syncwarp();
         while (sp > 0) {
             sp--;
             const int x0 = stack[sp][0], y0 = stack[sp][1], z0 = stack[sp][2], ex = stack[sp][3], ey = stack[sp][4], ez = stack[sp][5];
             __syncwarp();
-            const uint32_t nq = plan_row_sum(q_first, g, x0, x0 + ex, y0, ey, z0, ez, lane);
+            const uint32_t nq = plan_rows(q_first, g, x0, x0 + ex, y0, ey, z0, ez, lane);
             if (nq == 0) continue;
-            const uint32_t nc = plan_row_sum(c_first, g, max(x0 - 2, 0), min(x0 + ex + 2, g.nx), y0 - 2, ey + 4, z0 - 2, ez + 4, lane);
+            const uint32_t nc = plan_rows(c_first, g, max(x0 - 2, 0), min(x0 + ex + 2, g.nx), y0 - 2, ey + 4, z0 - 2, ez + 4, lane);
             uint32_t flags = 0;
             if (nc > (uint32_t)slab_cap) {
                 if (ex > 1 || ey > 1 || ez > 1) {
@@ -264,17 +257,17 @@ __device__ __noinline__ void brick_slow_query(const BrickArgs& a, float qx, floa
                 const int y = cy + dy;
                 if (y < 0 || y >= a.g.ny) continue;
                 const uint32_t key0 = ((uint32_t)z * (uint32_t)a.g.ny + (uint32_t)y) * (uint32_t)a.g.nx;
-                const uint32_t lo = a.c_first[key0 + max(cx - 2, 0)], hi = a.c_first[key0 + min(cx + 3, a.g.nx)];
+                const uint32_t lo = a.c.first[key0 + max(cx - 2, 0)], hi = a.c.first[key0 + min(cx + 3, a.g.nx)];
                 for (uint32_t t0 = lo; t0 < hi; t0 += 32) {
                     const uint32_t t = t0 + lane;
                     bool hit = false;
                     int id = -1;
                     if (t < hi) {
-                        const float4 v = a.c_pts[t];
+                        const float4 v = a.c.pts[t];
                         id = __float_as_int(v.w);
                         const float d2 = dist2(qx, qy, qz, v.x, v.y, v.z);
                         hit = d2 <= r2;
-                        if (SYMMETRIC) hit = hit || (d2 <= a.c_r2[t]);
+                        if (SYMMETRIC) hit = hit || (d2 <= a.c.r2[t]);
                         if (a.same_set && id == qid) hit = false;
                     }
                     const unsigned m = __ballot_sync(kFull, hit);
@@ -302,311 +295,382 @@ __device__ __noinline__ void brick_slow_query(const BrickArgs& a, float qx, floa
     }
 }
 
+
 // ---------------------------------------------------------------------------------------------------------------------------
-template <int NWARPS, int MINBLOCKS, bool VARIABLE, bool SYMMETRIC>
-__global__ void __launch_bounds__(NWARPS * 32, MINBLOCKS) brick_query_kernel(const BrickArgs a)
+// warps 0 .. NCONS-1 consume, warp NCONS + b produces into slab buffer b
+template <int NCONS, int SLAB, int KMAX, bool VARIABLE, bool SYMMETRIC>
+__global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const BrickArgs a)
 {
+    typedef BrickSmem<SLAB, KMAX, SYMMETRIC> SM;
     extern __shared__ __align__(128) unsigned char s_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const BrickLayout L = brick_layout(a.slab_cap, a.kmax, NWARPS, SYMMETRIC);
     const uint32_t s_base = smem_u32(s_raw);
-    const uint32_t slab_a = s_base + L.off_slab;
-    const uint32_t r2_a = s_base + L.off_r2;
-    const uint32_t dummy_off = (uint32_t)a.slab_cap * 16u;                 // byte offset of the dummy records inside the slab
-    uint16_t* const sT = reinterpret_cast<uint16_t*>(s_raw + L.off_T);
-    uint32_t* const s_rowkey = reinterpret_cast<uint32_t*>(s_raw + L.off_rowkey);
-    uint32_t* const s_g0 = reinterpret_cast<uint32_t*>(s_raw + L.off_g0);
-    uint32_t* const s_rowoff = reinterpret_cast<uint32_t*>(s_raw + L.off_rowoff);
-    uint32_t* const s_qs = reinterpret_cast<uint32_t*>(s_raw + L.off_qs);
-    uint32_t* const s_qoff = reinterpret_cast<uint32_t*>(s_raw + L.off_qoff);
-    int* const s_qdelta = reinterpret_cast<int*>(s_raw + L.off_qdelta);
-    uint32_t* const s_qrow = reinterpret_cast<uint32_t*>(s_raw + L.off_qrow);
-    uint32_t* const s_misc = reinterpret_cast<uint32_t*>(s_raw + L.off_misc);    // [0,1] mbarrier, [2] task, [3] next warp task, [4] n queries, [5] slab count
-    const uint32_t bar = s_base + L.off_misc;
-    const uint32_t tab_a = s_base + L.off_warp + warp * L.warp_bytes + lane * 4;  // this lane's column of the range table
-    const uint32_t col_w = s_base + L.off_warp + warp * L.warp_bytes + L.tab_bytes;
-    const uint32_t col_a = col_w + lane * 2;                                       // this lane's hit column
-    const uint32_t col_cap = col_a + (uint32_t)a.kmax * kColStride;
-
+    const uint32_t bars = s_base + SM::kOffBars;          // full[b] = bars + 8 b, empty[b] = bars + 16 + 8 b
     const BrickGrid g = a.g;
-    const bool same_set = a.same_set != 0;
-    const int query_limit = a.query_limit;
-    unsigned nb_sum = 0, slow_sum = 0;
 
-    for (int k = tid; k < kDummy; k += NWARPS * 32) {
-        reinterpret_cast<float4*>(s_raw + L.off_slab)[a.slab_cap + k] = make_float4(3.0e38f, 0.0f, 0.0f, __int_as_float(-1));
-        if (SYMMETRIC) reinterpret_cast<float*>(s_raw + L.off_r2)[a.slab_cap + k] = -1.0f;
+    // dummy records of both buffers, barriers
+    for (int k = tid; k < 2 * kDummy; k += (NCONS + 2) * 32) {
+        const int b = k / kDummy, i = k % kDummy;
+        reinterpret_cast<float4*>(s_raw + b * SM::kBufBytes + SM::kOffSlab)[SLAB + i] = make_float4(3.0e38f, 0.0f, 0.0f, __int_as_float(-1));
+        if (SYMMETRIC) reinterpret_cast<float*>(s_raw + b * SM::kBufBytes + SM::kOffR2)[SLAB + i] = -1.0f;
     }
-    if (tid == 0) mbar_init(bar, 1);
+    if (tid == 0) {
+        mbar_init(bars + 0, 1);
+        mbar_init(bars + 8, 1);
+        mbar_init(bars + 16, NCONS);
+        mbar_init(bars + 24, NCONS);
+        mbar_fence_init();
+    }
     __syncthreads();
-    uint32_t parity = 0;
     const uint32_t n_tasks = min(*a.n_tasks, a.max_tasks);
 
-    for (;;) {
-        if (tid == 0) s_misc[2] = atomicAdd(a.ticket, 1u);
-        __syncthreads();                    // every warp is done with the previous brick's slab, tables and counters
-        const uint32_t task = s_misc[2];
-        if (task >= n_tasks) break;
-        const BrickTask bt = a.tasks[task];
-        const int x0 = bt.x0, y0 = bt.y0, z0 = bt.z0;
-        const int ex = (int)(bt.dims & 0xffu), ey = (int)((bt.dims >> 8) & 0xffu), ez = (int)((bt.dims >> 16) & 0xffu);
-        const bool slow_brick = (bt.dims & kBrickSlow) != 0;
-        const int sy_n = ey + 4, n_rows = sy_n * (ez + 4), n_qrows = ey * ez, tw = ex + 5;
-
-        // ---- stage: row boundaries from the prefix table, one bulk copy per slab row (warp 0); query rows (warp 1)
-        if (warp == 0) {
-            const int xa = max(x0 - 2, 0), xb = min(x0 + ex + 2, g.nx);
-            uint32_t len[2], g0v[2];
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                const int r = lane + 32 * k;
-                len[k] = 0; g0v[k] = 0;
-                if (r < n_rows) {
-                    const int y = y0 - 2 + r % sy_n, z = z0 - 2 + r / sy_n;
-                    uint32_t key0 = 0xffffffffu;
-                    if (y >= 0 && y < g.ny && z >= 0 && z < g.nz) {
-                        key0 = ((uint32_t)z * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nx;
-                        g0v[k] = a.c_first[key0 + xa];
-                        len[k] = a.c_first[key0 + xb] - g0v[k];
-                    }
-                    s_rowkey[r] = key0;
-                    s_g0[r] = g0v[k];
+    if (warp >= NCONS) {
+        // =============================================== PRODUCER of buffer b ===============================================
+        const uint32_t b = (uint32_t)(warp - NCONS);
+        unsigned char* const buf = s_raw + b * SM::kBufBytes;
+        const uint32_t buf_a = s_base + b * SM::kBufBytes;
+        uint32_t* const meta = reinterpret_cast<uint32_t*>(buf + SM::kOffMeta);
+        uint32_t* const s_rowkey = reinterpret_cast<uint32_t*>(buf + SM::kOffRowKey);
+        int* const s_rowbase = reinterpret_cast<int*>(buf + SM::kOffRowBase);
+        uint16_t* const sT = reinterpret_cast<uint16_t*>(buf + SM::kOffT);
+        const uint32_t full = bars + 8 * b, empty = bars + 16 + 8 * b;
+        for (uint32_t use = 0;; use++) {
+            if (use >= 1) mbar_wait(empty, (use - 1u) & 1u);          // every consumer warp has left the brick that used this buffer
+            uint32_t task = 0;
+            if (lane == 0) task = atomicAdd(a.ticket, 1u);
+            task = __shfl_sync(kFull, task, 0);
+            if (task >= n_tasks) {
+                if (lane == 0) {
+                    meta[7] = 1u;
+                    mbar_arrive(full);
                 }
+                break;
+            }
+            const BrickTask bt = a.tasks[task];
+            const int x0 = bt.x0, y0 = bt.y0, z0 = bt.z0;
+            const int ex = (int)(bt.dims & 0xffu), ey = (int)((bt.dims >> 8) & 0xffu), ez = (int)((bt.dims >> 16) & 0xffu);
+            const bool slow_brick = (bt.dims & kBrickSlow) != 0;
+            const int tw = ex + 5;
+            const int xa = max(x0 - 2, 0), xb = min(x0 + ex + 2, g.nx);
+            // ---- slab rows: rows lane and lane + 32 (row = sz * 8 + sy)
+            uint32_t len[2], g0[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int r = lane + 32 * h;
+                const int sy = r & 7, sz = r >> 3;
+                const int y = y0 - 2 + sy, z = z0 - 2 + sz;
+                len[h] = 0; g0[h] = 0;
+                uint32_t key0 = 0xffffffffu;
+                if (!slow_brick && sy < ey + 4 && sz < ez + 4 && y >= 0 && y < g.ny && z >= 0 && z < g.nz) {
+                    key0 = ((uint32_t)z * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nx;
+                    g0[h] = a.c.first[key0 + xa];
+                    len[h] = a.c.first[key0 + xb] - g0[h];
+                    if (len[h] == 0) key0 = 0xffffffffu;
+                }
+                s_rowkey[r] = key0;
             }
             const uint32_t inc0 = (uint32_t)warp_inclusive_scan((int)len[0], lane);
             const uint32_t tot0 = __shfl_sync(kFull, inc0, 31);
             const uint32_t inc1 = (uint32_t)warp_inclusive_scan((int)len[1], lane) + tot0;
             const uint32_t total = __shfl_sync(kFull, inc1, 31);
-            const uint32_t off[2] = { inc0 - len[0], inc1 - len[1] };
-            if (lane < n_rows) s_rowoff[lane] = off[0];
-            if (lane + 32 < n_rows) s_rowoff[lane + 32] = off[1];
-            const bool fits = !slow_brick && total <= (uint32_t)a.slab_cap;
-            if (lane == 0) {
-                s_misc[5] = fits ? total : 0xffffffffu;
-                fence_proxy_async();        // the previous brick's generic reads of the slab are ordered before the async writes
-                mbar_arrive_expect_tx(bar, fits ? total * 16u : 0u);
-            }
-            __syncwarp();
-            if (fits) {
-#pragma unroll
-                for (int k = 0; k < 2; k++)
-                    if (len[k] > 0) bulk_g2s(slab_a + off[k] * 16u, a.c_pts + g0v[k], len[k] * 16u, bar);
-            }
-        } else if (warp == 1) {
-            uint32_t qs = 0, cnt = 0;
-            if (lane < n_qrows) {
-                const int ry = lane % ey, rz = lane / ey;
-                const uint32_t key0 = ((uint32_t)(z0 + rz) * (uint32_t)g.ny + (uint32_t)(y0 + ry)) * (uint32_t)g.nx;
-                qs = a.q_first[key0 + x0];
-                cnt = a.q_first[key0 + x0 + ex] - qs;
-                s_qs[lane] = qs;
-                s_qrow[lane] = (uint32_t)ry | ((uint32_t)rz << 8);
-            }
-            const uint32_t inc = (uint32_t)warp_inclusive_scan((int)cnt, lane);
-            const uint32_t nq_all = __shfl_sync(kFull, inc, 31);
-            if (lane < n_qrows) s_qoff[lane] = inc - cnt;
-            if (lane == n_qrows) s_qoff[lane] = nq_all;
-            if (lane == 0) { s_misc[4] = nq_all; s_misc[3] = 0u; }
-        }
-        __syncthreads();                    // row offsets visible
-        const bool staged = s_misc[5] != 0xffffffffu;
-        // ---- cell boundary table: T[row][i] = slab position of the first record of cell x0 - 2 + i of that row
-        if (staged) {
-            for (int e = tid; e < n_rows * tw; e += NWARPS * 32) {
-                const int r = e / tw, i = e - r * tw;
-                const uint32_t key0 = s_rowkey[r];
-                uint32_t v = s_rowoff[r];
-                if (key0 != 0xffffffffu) v += a.c_first[key0 + (uint32_t)min(max(x0 - 2 + i, 0), g.nx)] - s_g0[r];
-                sT[r * kTW + i] = (uint16_t)v;
-            }
-            if (SYMMETRIC) {
-                float* const sr2 = reinterpret_cast<float*>(s_raw + L.off_r2);
-                for (int r = warp; r < n_rows; r += NWARPS) {
-                    const uint32_t key0 = s_rowkey[r];
-                    if (key0 == 0xffffffffu) continue;
-                    const uint32_t o = s_rowoff[r], g0 = s_g0[r];
-                    const uint32_t n = ((r + 1 < n_rows) ? s_rowoff[r + 1] : s_misc[5]) - o;
-                    for (uint32_t k = lane; k < n; k += 32) sr2[o + k] = a.c_r2[g0 + k];
+            const uint32_t ro[2] = { inc0 - len[0], inc1 - len[1] };
+            s_rowbase[lane] = (int)ro[0] - (int)g0[0];
+            s_rowbase[lane + 32] = (int)ro[1] - (int)g0[1];
+            const bool staged = !slow_brick && total <= (uint32_t)SLAB;
+            // ---- query rows (row = rz * 4 + ry)
+            {
+                uint32_t qs = 0, cnt = 0;
+                const int ry = lane & 3, rz = lane >> 2;
+                if (lane < kQRows && ry < ey && rz < ez) {
+                    const uint32_t key0 = ((uint32_t)(z0 + rz) * (uint32_t)g.ny + (uint32_t)(y0 + ry)) * (uint32_t)g.nx;
+                    qs = a.q.first[key0 + x0];
+                    cnt = a.q.first[key0 + x0 + ex] - qs;
+                }
+                const uint32_t inc = (uint32_t)warp_inclusive_scan((int)cnt, lane);
+                const uint32_t nq_all = __shfl_sync(kFull, inc, 31);
+                if (lane < kQRows) { meta[8 + lane] = qs; meta[24 + lane] = inc - cnt; }
+                if (lane == kQRows) meta[24 + lane] = nq_all;
+                if (lane == 0) {
+                    meta[0] = (uint32_t)x0; meta[1] = (uint32_t)y0; meta[2] = (uint32_t)z0; meta[3] = bt.dims;
+                    meta[4] = nq_all; meta[5] = staged ? 1u : 0u; meta[6] = 0u; meta[7] = 0u;
                 }
             }
-            if (same_set && tid < n_qrows) {
-                const uint32_t qr = s_qrow[tid];
-                const int srow = ((int)(qr >> 8) + 2) * sy_n + (int)(qr & 0xffu) + 2;
-                s_qdelta[tid] = (int)s_rowoff[srow] - (int)s_g0[srow];
-            }
-        }
-        __syncthreads();                    // tables visible
-        mbar_wait(bar, parity);             // slab rows have landed
-        parity ^= 1u;
-        const int nq = (int)s_misc[4];
-
-        // ---- warp tasks: 32 consecutive queries of the brick
-        for (;;) {
-            int wt = 0;
-            if (lane == 0) wt = (int)atomicAdd(&s_misc[3], 1u);
-            wt = __shfl_sync(kFull, wt, 0);
-            if (wt * 32 >= nq) break;
-            const int ci = wt * 32 + lane;
-            const bool has = ci < nq;
-            int rr = 0;
-            for (int k = 1; k < n_qrows; k++) rr += (ci >= (int)s_qoff[k]) ? 1 : 0;
-            const uint32_t qrow = s_qrow[rr];
-            const int ry = (int)(qrow & 0xffu), rz = (int)(qrow >> 8);
-            const int qp = has ? (int)s_qs[rr] + (ci - (int)s_qoff[rr]) : 0;
-            float4 q = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0x7fffffff));
-            float r2 = a.r2_fixed;
-            if (has) {
-                q = a.q_pts[qp];
-                if (VARIABLE) r2 = a.q_r2[qp];
-            }
-            const int qid = __float_as_int(q.w);
-            const bool active = has && qid < query_limit;
-            double tx, ty, tz;
-            const int cx = brick_cell(q.x, g.bottom[0], g.inv_cell, g.nx, tx);
-            (void)brick_cell(q.y, g.bottom[1], g.inv_cell, g.ny, ty);
-            (void)brick_cell(q.z, g.bottom[2], g.inv_cell, g.nz, tz);
-            const int cy = y0 + ry, cz = z0 + rz;
-            bool slow = active && (slow_brick || !staged);
-            int n = 0;
-
-            uint32_t total = 0;
-            int n_ent = 0;
+            __syncwarp();
+            if (lane < kQRows) meta[44 + lane] = (uint32_t)s_rowbase[((lane >> 2) + 2) * kRowPitch + (lane & 3) + 2];
             if (staged) {
-                // ---- this lane's candidate ranges: rows within the search distance, x extent culled per row
-                const float fx = (float)(tx - (double)cx), fy = (float)(ty - (double)cy), fz = (float)(tz - (double)cz);
-                float cull = a.cull_r2;
-                if (VARIABLE && !SYMMETRIC) {
-                    const float rc = __fmul_rn(sqrtf(r2), a.inv_cell_f);
-                    cull = __fmul_rn(__fmul_rn(rc, rc), 1.002f);
+                // ---- the copies first (they run while the boundary table is built), then T; the producer's ARRIVAL on `full` comes
+                // last (release: meta and T are visible to a consumer that sees the phase complete)
+                if (lane == 0) {
+                    fence_proxy_async();    // the consumers' generic reads of this buffer (ordered by the empty barrier) precede the async writes
+                    mbar_expect_tx(full, total * 16u);
                 }
-                const int ix = min(max(cx - x0, 0), ex - 1);
-                float dd[5];
-                dd[0] = fy + 1.0f; dd[1] = fy; dd[2] = 0.0f; dd[3] = 1.0f - fy; dd[4] = 2.0f - fy;
-                float ddz[5];
-                ddz[0] = fz + 1.0f; ddz[1] = fz; ddz[2] = 0.0f; ddz[3] = 1.0f - fz; ddz[4] = 2.0f - fz;
+                __syncwarp();
 #pragma unroll
-                for (int k = 0; k < 5; k++) { dd[k] = dd[k] * dd[k]; ddz[k] = ddz[k] * ddz[k]; }
-                const int self_pos = same_set ? qp + s_qdelta[rr] : -1;
+                for (int h = 0; h < 2; h++) {
+                    if (len[h] == 0) continue;
+                    bulk_g2s(buf_a + SM::kOffSlab + ro[h] * 16u, a.c.pts + g0[h], len[h] * 16u, full);
+                }
+                if (SYMMETRIC) {
+                    // r^2 of the rows' records: plain coalesced loads, one row per iteration (4-byte elements have no 16-byte
+                    // alignment to offer a bulk copy)
+                    float* const sr2 = reinterpret_cast<float*>(buf + SM::kOffR2);
+#pragma unroll 4
+                    for (int r = 0; r < kSlabRows; r++) {
+                        const uint32_t lr = __shfl_sync(kFull, len[r >> 5], r & 31), gr = __shfl_sync(kFull, g0[r >> 5], r & 31), rr_ = __shfl_sync(kFull, ro[r >> 5], r & 31);
+                        for (uint32_t k = lane; k < lr; k += 32) sr2[rr_ + k] = a.c.r2[gr + k];
+                    }
+                }
+                // T[row][i] = slab position of the first record of cell x0 - 2 + i of that row: one row per load instruction (lane = i),
+                // eight rows in flight
+                const int n_rows = (ez + 4) * kRowPitch;
+                const int xi0 = min(max(x0 - 2 + lane, 0), g.nx), xi1 = min(max(x0 - 2 + lane + 32, 0), g.nx);
+                for (int r0 = 0; r0 < n_rows; r0 += 8) {
+                    uint32_t v0[8], v1[8];
 #pragma unroll
-                for (int dz = 0; dz < 5; dz++) {
-#pragma unroll
-                    for (int dy = 0; dy < 5; dy++) {
-                        const float d2yz = dd[dy] + ddz[dz];
-                        const float h = sqrtf(fmaxf(cull - d2yz, 0.0f)) + 1.0e-4f;
-                        const int xlo = max(__float2int_rd(fx - h), -2), xhi = min(__float2int_rd(fx + h), 2);
-                        const uint16_t* trow = sT + ((rz + dz) * sy_n + (ry + dy)) * kTW + ix;
-                        int lo = (int)trow[xlo + 2], hi = (int)trow[xhi + 3];
-                        if (!(active && d2yz <= cull)) hi = lo;
-                        if (dy == 2 && dz == 2 && self_pos >= lo && self_pos < hi) {
-                            // own row: the query's own record is cut out (only the identical (set, index) is excluded, TreeNSearch.cpp:2464-2466)
-                            if (self_pos > lo) {
-                                sts_u32(tab_a + n_ent * 128, ((uint32_t)lo * 16u) | (((uint32_t)self_pos * 16u) << 16));
-                                n_ent++;
-                                total += (uint32_t)(self_pos - lo);
-                            }
-                            lo = self_pos + 1;
-                        }
-                        if (hi > lo) {
-                            sts_u32(tab_a + n_ent * 128, ((uint32_t)lo * 16u) | (((uint32_t)hi * 16u) << 16));
-                            n_ent++;
-                            total += (uint32_t)(hi - lo);
+                    for (int j = 0; j < 8; j++) {
+                        const uint32_t key0 = s_rowkey[r0 + j];
+                        v0[j] = 0; v1[j] = 0;
+                        if (key0 != 0xffffffffu) {
+                            v0[j] = a.c.first[key0 + (uint32_t)xi0];
+                            if (lane + 32 < tw) v1[j] = a.c.first[key0 + (uint32_t)xi1];
                         }
                     }
-                }
-                if (total > (uint32_t)kMaxTot) { slow = true; total = 0; n_ent = 0; }
-            }
-            const int maxtot = (int)__reduce_max_sync(kFull, total);
-            if (maxtot > 0) {
-                // lanes with fewer candidates walk the dummy records (never a hit) until the longest lane is done
-                int pad = maxtot - (int)total;
-                while (pad > 0) {
-                    const int c = min(pad, kDummy);
-                    sts_u32(tab_a + n_ent * 128, dummy_off | ((dummy_off + (uint32_t)c * 16u) << 16));
-                    n_ent++;
-                    pad -= c;
-                }
-                sts_u32(tab_a + n_ent * 128, dummy_off | ((dummy_off + (uint32_t)kDummy * 16u) << 16));     // landing entry of the last advance
-
-                // ---- the flattened candidate walk
-                uint32_t w = lds_u32(tab_a);
-                uint32_t p = w & 0xffffu, e = w >> 16;
-                uint32_t wn = lds_u32(tab_a + 128);
-                uint32_t rp = tab_a + 256;
-                uint32_t ca = col_a;
-                float4 c = lds_f4(slab_a + p);
-#pragma unroll 2
-                for (int it = 0; it < maxtot; it++) {
-                    const uint32_t pc = p;
-                    p += 16u;
-                    if (p == e) {
-                        p = wn & 0xffffu;
-                        e = wn >> 16;
-                        wn = lds_u32(rp);
-                        rp += 128u;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int r = r0 + j;
+                        const bool ok = s_rowkey[r] != 0xffffffffu;
+                        const int rb = s_rowbase[r];
+                        sT[r * kTW + lane] = ok ? (uint16_t)(((int)v0[j] + rb) * 16) : (uint16_t)0;
+                        if (lane + 32 < kTW) sT[r * kTW + lane + 32] = (ok && lane + 32 < tw) ? (uint16_t)(((int)v1[j] + rb) * 16) : (uint16_t)0;
                     }
-                    const float4 cn = lds_f4(slab_a + p);
-                    const float d2 = dist2(q.x, q.y, q.z, c.x, c.y, c.z);
-                    bool hit = d2 <= r2;
-                    if (SYMMETRIC) hit = hit || (d2 <= lds_f32(r2_a + (pc >> 2)));
-                    if (hit) {
-                        sts_u16(ca, pc);
-                        ca = min(ca + (uint32_t)kColStride, col_cap);
-                    }
-                    c = cn;
                 }
-                n = (int)((ca - col_a) / (uint32_t)kColStride);
-                if (active && !slow && ca == col_cap) slow = true;          // the column is full: the list may be longer
-            }
-
-            // ---- publish the 32 lists: [n, j0, j1, ...] back to back, one reservation per warp
-            const bool valid = active && !slow;
-            const int words = valid ? n + 1 : 0;
-            const int inc = warp_inclusive_scan(words, lane);
-            const int W = __shfl_sync(kFull, inc, 31);
-            const int off = inc - words;
-            __syncwarp();
-            if (W > 0) {
-                const unsigned long long need = (unsigned long long)((W + 3) & ~3);
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(a.cursor, need);
-                base = __shfl_sync(kFull, base, 0);
-                if ((long long)(base + need) <= a.capacity) {
-                    if (valid) a.list_pos[qid] = (long long)base + off;
-                    int32_t* const out = a.ragged + base;
-                    for (int k = 0; k < 32; k++) {
-                        const int wk = __shfl_sync(kFull, words, k);
-                        if (wk == 0) continue;
-                        const int ok = __shfl_sync(kFull, off, k);
-                        for (int u = lane; u < wk; u += 32) {
-                            int v = wk - 1;
-                            if (u > 0) v = (int)lds_u32(slab_a + lds_u16(col_w + (uint32_t)(u - 1) * kColStride + (uint32_t)k * 2u) + 12u);
-                            __stcs(out + ok + u, v);
-                        }
-                    }
-                } else if (lane == 0) {
-                    *a.overflow = 1;
-                }
-                nb_sum += (unsigned)(W - __popc(__ballot_sync(kFull, valid)));
-            }
-            // ---- slow path queries, one at a time
-            unsigned sm = __ballot_sync(kFull, slow);
-            while (sm) {
-                const int src = __ffs(sm) - 1;
-                sm &= sm - 1;
-                brick_slow_query<SYMMETRIC>(a, __shfl_sync(kFull, q.x, src), __shfl_sync(kFull, q.y, src), __shfl_sync(kFull, q.z, src), __shfl_sync(kFull, qid, src),
-                                            __shfl_sync(kFull, r2, src), __shfl_sync(kFull, cx, src), __shfl_sync(kFull, cy, src), __shfl_sync(kFull, cz, src), lane, nb_sum);
-                slow_sum++;
-            }
-            if (nb_sum > 0x40000000u) {
-                if (lane == 0) atomicAdd(a.n_neighbors, (unsigned long long)nb_sum);
-                nb_sum = 0;
             }
             __syncwarp();
+            if (lane == 0) mbar_arrive(full);
         }
-    }
-    if (lane == 0) {
-        if (nb_sum) atomicAdd(a.n_neighbors, (unsigned long long)nb_sum);
-        if (slow_sum) atomicAdd(a.n_slow, (unsigned long long)slow_sum);
+    } else {
+        // =============================================== CONSUMERS ===============================================
+        const uint32_t tab_a = s_base + SM::kOffWarp + warp * SM::kWarpBytes + lane * 4;      // this lane's column of the range table
+        const uint32_t col_w = s_base + SM::kOffWarp + warp * SM::kWarpBytes + SM::kTabBytes;
+        const uint32_t col_a = col_w + lane * 2;                                                // this lane's hit column
+        const uint32_t col_cap = col_a + (uint32_t)KMAX * kColStride;
+        const bool same_set = a.same_set != 0;
+        const int query_limit = a.query_limit;
+        constexpr uint32_t kDummyOff = (uint32_t)SLAB * 16u;
+        unsigned nb_sum = 0, slow_sum = 0;
+
+        // one brick out of slab buffer B (B is a compile time constant: shared memory addresses fold into the load instructions);
+        // returns false when the producer of this buffer has signalled the end of the task list
+        auto consume = [&](auto btag, uint32_t use) -> bool {
+            constexpr int B = decltype(btag)::value;
+            unsigned char* const buf = s_raw + B * SM::kBufBytes;
+            const uint32_t buf_a = s_base + B * SM::kBufBytes;
+            uint32_t* const meta = reinterpret_cast<uint32_t*>(buf + SM::kOffMeta);
+            const uint16_t* const sT = reinterpret_cast<const uint16_t*>(buf + SM::kOffT);
+            mbar_wait(bars + 8 * B, use & 1u);                  // tables written, slab rows landed
+            if (meta[7]) return false;
+            const int x0 = (int)meta[0], y0 = (int)meta[1], z0 = (int)meta[2];
+            const int ex = (int)(meta[3] & 0xffu);
+            const bool staged = meta[5] != 0u;
+            const int nq = (int)meta[4];
+            const uint32_t slab_a = buf_a + SM::kOffSlab;
+
+            for (;;) {
+                int wt = 0;
+                if (lane == 0) wt = (int)atomicAdd(&meta[6], 1u);
+                wt = __shfl_sync(kFull, wt, 0);
+                if (wt * 32 >= nq) break;
+                const int ci = wt * 32 + lane;
+                const bool has = ci < nq;
+                int rr = 0;
+#pragma unroll
+                for (int k = 1; k < kQRows; k++) rr += (ci >= (int)meta[24 + k]) ? 1 : 0;
+                const int ry = rr & 3, rz = rr >> 2;
+                const int qp = has ? (int)meta[8 + rr] + (ci - (int)meta[24 + rr]) : 0;
+                float4 q = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0x7fffffff));
+                float r2 = a.r2_fixed;
+                if (has) {
+                    q = a.q.pts[qp];
+                    if (VARIABLE) r2 = a.q.r2[qp];
+                }
+                const int qid = __float_as_int(q.w);
+                const bool active = has && qid < query_limit;
+                double tx, ty, tz;
+                const int cx = brick_cell(q.x, g.bottom[0], g.inv_cell, g.nx, tx);
+                (void)brick_cell(q.y, g.bottom[1], g.inv_cell, g.ny, ty);
+                (void)brick_cell(q.z, g.bottom[2], g.inv_cell, g.nz, tz);
+                const int cy = y0 + ry, cz = z0 + rz;
+                bool slow = active && !staged;
+                uint32_t total = 0;
+                uint32_t tp = tab_a;                                // next free entry of this lane's range table
+                if (staged) {
+                    // ---- this lane's candidate ranges: rows within the search distance, cells culled per row
+                    const float fx = (float)(tx - (double)cx), fy = (float)(ty - (double)cy), fz = (float)(tz - (double)cz);
+                    float cull = a.cull_r2;
+                    if (VARIABLE && !SYMMETRIC) {
+                        const float rc = __fmul_rn(sqrtf(r2), a.inv_cell_f);
+                        cull = __fmul_rn(__fmul_rn(rc, rc), 1.002f);
+                    }
+                    if (!active) cull = -1.0f;
+                    const int ix = min(max(cx - x0, 0), ex - 1);
+                    // squared distance of the query to the slabs of cells at offset -2, -1, 0, +1, +2 along y and z ...
+                    float dy2[5], dz2[5];
+                    dy2[0] = fy + 1.0f; dy2[1] = fy; dy2[2] = 0.0f; dy2[3] = 1.0f - fy; dy2[4] = 2.0f - fy;
+                    dz2[0] = fz + 1.0f; dz2[1] = fz; dz2[2] = 0.0f; dz2[3] = 1.0f - fz; dz2[4] = 2.0f - fz;
+#pragma unroll
+                    for (int k = 0; k < 5; k++) { dy2[k] = dy2[k] * dy2[k]; dz2[k] = dz2[k] * dz2[k]; }
+                    // ... and to the cells at x offset -2, -1, +1, +2: cell k of a row is needed iff dx2[k] + d2yz <= cull
+                    const float ax0 = (fx + 1.0f) * (fx + 1.0f), ax1 = fx * fx, ax2 = (1.0f - fx) * (1.0f - fx), ax3 = (2.0f - fx) * (2.0f - fx);
+                    const int self_pos = same_set ? (qp + (int)meta[44 + rr]) * 16 : -1;        // T holds byte offsets into the slab
+                    const uint16_t* const tq = sT + (rz * kRowPitch + ry) * kTW + ix;
+#pragma unroll
+                    for (int dz = 0; dz < 5; dz++) {
+#pragma unroll
+                        for (int dy = 0; dy < 5; dy++) {
+                            const float rem = cull - (dy2[dy] + dz2[dz]);
+                            const int i_lo = 2 - ((rem >= ax1) ? 1 : 0) - ((rem >= ax0) ? 1 : 0);
+                            const int i_hi = 3 + ((rem >= ax2) ? 1 : 0) + ((rem >= ax3) ? 1 : 0);
+                            const uint16_t* const trow = tq + (dz * kRowPitch + dy) * kTW;
+                            uint32_t lo = trow[i_lo];
+                            const uint32_t hi = trow[i_hi];
+                            const bool row_ok = rem >= 0.0f;
+                            if (dy == 2 && dz == 2 && row_ok && self_pos >= (int)lo && self_pos < (int)hi) {
+                                // own row: the query's own record is cut out (only the identical (set, index) is excluded, TreeNSearch.cpp:2464-2466)
+                                if (self_pos > (int)lo) {
+                                    sts_u32(tp, lo | ((uint32_t)self_pos << 16));
+                                    tp += 128u;
+                                    total += (uint32_t)self_pos - lo;
+                                }
+                                lo = (uint32_t)self_pos + 16u;
+                            }
+                            if (row_ok && hi > lo) {
+                                sts_u32(tp, lo | (hi << 16));
+                                tp += 128u;
+                                total += hi - lo;
+                            }
+                        }
+                    }
+                    total >>= 4;        // bytes -> records
+                    if (total > (uint32_t)kMaxTot) { slow = true; total = 0; tp = tab_a; }
+                }
+                const int maxtot = (int)__reduce_max_sync(kFull, total);
+                uint32_t ca = col_a;
+                if (maxtot > 0) {
+                    // lanes with fewer candidates walk the dummy records (never a hit) until the longest lane is done
+                    int pad = maxtot - (int)total;
+                    while (pad > 0) {
+                        const int c = min(pad, kDummy);
+                        sts_u32(tp, kDummyOff | ((kDummyOff + (uint32_t)c * 16u) << 16));
+                        tp += 128u;
+                        pad -= c;
+                    }
+                    sts_u32(tp, kDummyOff | ((kDummyOff + (uint32_t)kDummy * 16u) << 16));      // landing entry of the last advance
+
+                    // ---- the flattened candidate walk
+                    uint32_t w = lds_u32(tab_a);
+                    uint32_t p = w & 0xffffu, e = w >> 16;
+                    uint32_t wn = lds_u32(tab_a + 128);
+                    uint32_t rp = tab_a + 256;
+                    float4 c = lds_f4(slab_a + p);
+#pragma unroll 4
+                    for (int it = 0; it < maxtot; it++) {
+                        const uint32_t pc = p;
+                        p += 16u;
+                        if (p == e) {
+                            p = wn & 0xffffu;
+                            e = wn >> 16;
+                            wn = lds_u32(rp);
+                            rp += 128u;
+                        }
+                        const float4 cn = lds_f4(slab_a + p);
+                        const float d2 = dist2(q.x, q.y, q.z, c.x, c.y, c.z);
+                        bool hit = d2 <= r2;
+                        if (SYMMETRIC) hit = hit || (d2 <= lds_f32(buf_a + SM::kOffR2 + (pc >> 2)));
+                        if (hit) {
+                            sts_u16(ca, pc);
+                            ca = min(ca + (uint32_t)kColStride, col_cap);
+                        }
+                        c = cn;
+                    }
+                    if (active && !slow && ca == col_cap) slow = true;          // the column is full: the list may be longer
+                }
+                const int n = (int)((ca - col_a) / (uint32_t)kColStride);
+
+                // ---- publish the 32 lists: [n, j0, j1, ...] back to back, one reservation per warp
+                const bool valid = active && !slow;
+                const int words = valid ? n + 1 : 0;
+                const int inc = warp_inclusive_scan(words, lane);
+                const int W = __shfl_sync(kFull, inc, 31);
+                const int off = inc - words;
+                __syncwarp();
+                if (W > 0) {
+                    const unsigned long long need = (unsigned long long)((W + 3) & ~3);
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(a.cursor, need);
+                    base = __shfl_sync(kFull, base, 0);
+                    if ((long long)(base + need) <= a.capacity) {
+                        if (valid) a.list_pos[qid] = (long long)base + off;
+                        // list k = column k of the hit table; (words, offset) of every list are broadcast through the (now idle) range
+                        // table instead of shuffles; one coalesced store per 32 list words
+                        sts_u32(tab_a, (uint32_t)words | ((uint32_t)off << 8));
+                        __syncwarp();
+                        int32_t* const out_l = a.ragged + base + lane;
+                        const uint32_t id_a = slab_a + 12u;
+                        const uint32_t tab_w = tab_a - (uint32_t)lane * 4u;
+                        uint32_t colk = col_w + (uint32_t)lane * kColStride - kColStride;       // entry (lane - 1) of column k
+#pragma unroll 1
+                        for (int k = 0; k < 32; k++, colk += 2u) {
+                            const uint32_t wo = lds_u32(tab_w + (uint32_t)k * 4u);
+                            const int wk = (int)(wo & 0xffu);
+                            int32_t* const o = out_l + (wo >> 8);
+                            if (lane < wk) {
+                                int v = wk - 1;
+                                if (lane > 0) v = (int)lds_u32(id_a + lds_u16(colk));
+                                __stcs(o, v);
+                            }
+                            if (lane + 32 < wk) __stcs(o + 32, (int)lds_u32(id_a + lds_u16(colk + 32u * kColStride)));
+                            if (KMAX > 63) {
+                                if (wk > 64) {
+                                    for (int u = lane + 64; u < wk; u += 32)
+                                        __stcs(o + (u - lane), (int)lds_u32(id_a + lds_u16(colk + (uint32_t)(u - lane) * kColStride)));
+                                }
+                            }
+                        }
+                    } else if (lane == 0) {
+                        *a.overflow = 1;
+                    }
+                    nb_sum += (unsigned)(W - __popc(__ballot_sync(kFull, valid)));
+                }
+                // ---- slow path queries, one at a time
+                unsigned sm = __ballot_sync(kFull, slow);
+                while (sm) {
+                    const int src = __ffs(sm) - 1;
+                    sm &= sm - 1;
+                    brick_slow_query<SYMMETRIC>(a, __shfl_sync(kFull, q.x, src), __shfl_sync(kFull, q.y, src), __shfl_sync(kFull, q.z, src), __shfl_sync(kFull, qid, src),
+                                                __shfl_sync(kFull, r2, src), __shfl_sync(kFull, cx, src), __shfl_sync(kFull, cy, src), __shfl_sync(kFull, cz, src), lane, nb_sum);
+                    slow_sum++;
+                }
+                if (nb_sum > 0x40000000u) {
+                    if (lane == 0) atomicAdd(a.n_neighbors, (unsigned long long)nb_sum);
+                    nb_sum = 0;
+                }
+                __syncwarp();
+            }
+            // this warp is done with the brick (and with its slab buffer)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + 16 + 8 * B);
+            return true;
+        };
+
+        bool live0 = true, live1 = true;
+        for (uint32_t use = 0; live0 || live1; use++) {
+            if (live0) live0 = consume(std::integral_constant<int, 0>{}, use);
+            if (live1) live1 = consume(std::integral_constant<int, 1>{}, use);
+        }
+        if (lane == 0) {
+            if (nb_sum) atomicAdd(a.n_neighbors, (unsigned long long)nb_sum);
+            if (slow_sum) atomicAdd(a.n_slow, (unsigned long long)slow_sum);
+        }
     }
 }
 

@@ -520,16 +520,31 @@ int build_sets_brick(tnsb_context* c, const BrickGrid& bg)
     return TNSB_OK;
 }
 
-// shared memory geometry of the brick query: records per slab and hits per lane column, chosen so that two CTAs of 8 warps
-// (kmax = 64) or one CTA of 12 warps (kmax = 128, dense clouds) fit an SM
-struct BrickConfig { int slab_cap, kmax, n_warps, blocks_per_sm; };
-BrickConfig brick_config(bool symmetric, int kmax)
+// Variants of the brick query (consumer warps, slab records per buffer, hits per lane column), sized so that one persistent CTA
+// fills the shared memory of an SM: the usual SPH densities (~30 neighbours) / dense clouds (lists up to 128 ids)
+template <bool SYM> struct BrickVariantA { static constexpr int kCons = 16, kSlab = SYM ? 1952 : 2496, kKmax = 64; };
+template <bool SYM> struct BrickVariantB { static constexpr int kCons = 12, kSlab = SYM ? 1488 : 1920, kKmax = 128; };
+
+BrickSet brick_set(const SetState& st)
 {
-    BrickConfig b;
-    b.kmax = kmax <= 64 ? 64 : 128;
-    if (b.kmax == 64) { b.n_warps = 8; b.blocks_per_sm = 2; b.slab_cap = symmetric ? 1792 : 2304; }
-    else { b.n_warps = 12; b.blocks_per_sm = 1; b.slab_cap = symmetric ? 2560 : 3072; }
-    return b;
+    BrickSet p;
+    p.pts = st.sorted.as<float4>();
+    p.r2 = st.sorted_r2.as<float>();
+    p.first = st.first.as<uint32_t>();
+    return p;
+}
+
+template <typename V, bool VARIABLE, bool SYM>
+cudaError_t launch_brick(const BrickArgs& a, int n_sms, cudaStream_t s)
+{
+    typedef BrickSmem<V::kSlab, V::kKmax, SYM> SM;
+    constexpr int smem = SM::total(V::kCons);
+    static_assert(smem <= 227 * 1024, "brick query variant exceeds the shared memory of an SM");
+    auto kernel = brick_query_kernel<V::kCons, V::kSlab, V::kKmax, VARIABLE, SYM>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<n_sms, (V::kCons + 2) * 32, smem, s>>>(a);
+    return cudaGetLastError();
 }
 
 int query_pair_brick(tnsb_context* c, int si, int sj, PairCounters* d_cnt)
@@ -539,16 +554,13 @@ int query_pair_brick(tnsb_context* c, int si, int sj, PairCounters* d_cnt)
     PairState& ps = c->pairs[si * c->sets.size() + sj];
     const bool variable = !c->radius_set;
     const bool symmetric = variable && c->symmetric;   // TreeNSearch.cpp:2431
-    const BrickConfig bc = brick_config(symmetric, c->brick_kmax);
+    const bool tall = c->brick_kmax > 64;
+    const int slab_cap = tall ? (symmetric ? BrickVariantB<true>::kSlab : BrickVariantB<false>::kSlab) : (symmetric ? BrickVariantA<true>::kSlab : BrickVariantA<false>::kSlab);
     const BrickGrid& bg = c->bgrid;
     BrickArgs a;
     a.g = bg;
-    a.q_pts = qi.sorted.as<float4>();
-    a.q_r2 = qi.sorted_r2.as<float>();
-    a.q_first = qi.first.as<uint32_t>();
-    a.c_pts = cj.sorted.as<float4>();
-    a.c_r2 = cj.sorted_r2.as<float>();
-    a.c_first = cj.first.as<uint32_t>();
+    a.q = brick_set(qi);
+    a.c = brick_set(cj);
     a.same_set = si == sj;
     a.query_limit = c->opt_query_limit >= 0 ? (int)std::min<int64_t>(c->opt_query_limit, INT_MAX) : INT_MAX;
     a.r2_fixed = c->radius_sq;
@@ -565,8 +577,6 @@ int query_pair_brick(tnsb_context* c, int si, int sj, PairCounters* d_cnt)
     a.n_tasks = &d_cnt->n_tasks;
     a.plan_overflow = &d_cnt->plan_overflow;
     a.ticket = &d_cnt->ticket;
-    a.slab_cap = bc.slab_cap;
-    a.kmax = bc.kmax;
     a.ragged = ps.in_host ? ps.h_ragged.as<int32_t>() : ps.d_ragged.as<int32_t>();
     a.capacity = ps.capacity;
     a.list_pos = ps.d_list_pos.as<long long>();
@@ -575,25 +585,17 @@ int query_pair_brick(tnsb_context* c, int si, int sj, PairCounters* d_cnt)
     a.n_slow = &d_cnt->n_slow;
     a.overflow = &d_cnt->overflow;
     cudaStream_t s = c->stream;
-    brick_plan_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(n_bricks, 8), 8 * c->n_sms), 256, 0, s>>>(bg, a.q_first, a.c_first, a.slab_cap, a.tasks, a.max_tasks, a.n_tasks, a.plan_overflow);
+    brick_plan_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(n_bricks, 8), 8 * c->n_sms), 256, 0, s>>>(bg, a.q.first, a.c.first, slab_cap, a.tasks, a.max_tasks, a.n_tasks, a.plan_overflow);
     TNSB_CUDA(c, cudaGetLastError());
-    const int smem = brick_layout(bc.slab_cap, bc.kmax, bc.n_warps, symmetric).total;
-    const int grid = c->n_sms * bc.blocks_per_sm;
-    auto go = [&](auto kernel) -> cudaError_t {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        kernel<<<grid, bc.n_warps * 32, smem, s>>>(a);
-        return cudaGetLastError();
-    };
     cudaError_t e;
-    if (bc.kmax == 64) {
-        if (!variable) e = go(brick_query_kernel<8, 2, false, false>);
-        else if (!symmetric) e = go(brick_query_kernel<8, 2, true, false>);
-        else e = go(brick_query_kernel<8, 2, true, true>);
+    if (!tall) {
+        if (!variable) e = launch_brick<BrickVariantA<false>, false, false>(a, c->n_sms, s);
+        else if (!symmetric) e = launch_brick<BrickVariantA<false>, true, false>(a, c->n_sms, s);
+        else e = launch_brick<BrickVariantA<true>, true, true>(a, c->n_sms, s);
     } else {
-        if (!variable) e = go(brick_query_kernel<12, 1, false, false>);
-        else if (!symmetric) e = go(brick_query_kernel<12, 1, true, false>);
-        else e = go(brick_query_kernel<12, 1, true, true>);
+        if (!variable) e = launch_brick<BrickVariantB<false>, false, false>(a, c->n_sms, s);
+        else if (!symmetric) e = launch_brick<BrickVariantB<false>, true, false>(a, c->n_sms, s);
+        else e = launch_brick<BrickVariantB<true>, true, true>(a, c->n_sms, s);
     }
     TNSB_CUDA(c, e);
     c->stats.n_kernel_launches += 2;
