@@ -78,6 +78,7 @@ struct BrickArgs {
     unsigned long long* cursor;
     unsigned long long* n_neighbors;
     unsigned long long* n_slow;
+    int* max_list;            // longest list written (atomicMax): picks the hit column height of the next run
     int* overflow;
 };
 
@@ -159,6 +160,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// -1 if a >= b else 0 (FSET: no predicate round trip)
+__device__ __forceinline__ int fge_mask(float a, float b)
+{
+    int d;
+    asm("set.ge.s32.f32 %0, %1, %2;" : "=r"(d) : "f"(a), "f"(b));
+    return d;
+}
+// streaming 32-bit store to base[off] / base[off + 32] (one mad.wide for the address)
+__device__ __forceinline__ void stg_cs_at(const int32_t* base, uint32_t off, int v)
+{
+    asm volatile("{\n.reg .u64 a;\nmad.wide.u32 a, %1, 4, %0;\nst.global.cs.s32 [a], %2;\n}\n" ::"l"(base), "r"(off), "r"(v) : "memory");
+}
+__device__ __forceinline__ void stg_cs_at32(const int32_t* base, uint32_t off, int v)
+{
+    asm volatile("{\n.reg .u64 a;\nmad.wide.u32 a, %1, 4, %0;\nst.global.cs.s32 [a+128], %2;\n}\n" ::"l"(base), "r"(off), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -304,7 +321,8 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
     typedef BrickSmem<SLAB, KMAX, SYMMETRIC> SM;
     extern __shared__ __align__(128) unsigned char s_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t s_base = smem_u32(s_raw);
+    uint32_t s_base = smem_u32(s_raw);
+    asm volatile("" : "+r"(s_base));                      // opaque: keeps the shared window base in a register instead of re-deriving it per access
     const uint32_t bars = s_base + SM::kOffBars;          // full[b] = bars + 8 b, empty[b] = bars + 16 + 8 b
     const BrickGrid g = a.g;
 
@@ -335,11 +353,12 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
         uint16_t* const sT = reinterpret_cast<uint16_t*>(buf + SM::kOffT);
         const uint32_t full = bars + 8 * b, empty = bars + 16 + 8 * b;
         for (uint32_t use = 0;; use++) {
-            if (use >= 1) mbar_wait(empty, (use - 1u) & 1u);          // every consumer warp has left the brick that used this buffer
+            // ---- everything that only needs registers happens BEFORE the wait for the buffer: next ticket, brick, row boundaries
             uint32_t task = 0;
             if (lane == 0) task = atomicAdd(a.ticket, 1u);
             task = __shfl_sync(kFull, task, 0);
             if (task >= n_tasks) {
+                if (use >= 1) mbar_wait(empty, (use - 1u) & 1u);
                 if (lane == 0) {
                     meta[7] = 1u;
                     mbar_arrive(full);
@@ -352,48 +371,51 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
             const bool slow_brick = (bt.dims & kBrickSlow) != 0;
             const int tw = ex + 5;
             const int xa = max(x0 - 2, 0), xb = min(x0 + ex + 2, g.nx);
-            // ---- slab rows: rows lane and lane + 32 (row = sz * 8 + sy)
-            uint32_t len[2], g0[2];
+            // slab rows: rows lane and lane + 32 (row = sz * 8 + sy)
+            uint32_t len[2], g0[2], rkey[2];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int r = lane + 32 * h;
                 const int sy = r & 7, sz = r >> 3;
                 const int y = y0 - 2 + sy, z = z0 - 2 + sz;
                 len[h] = 0; g0[h] = 0;
-                uint32_t key0 = 0xffffffffu;
+                rkey[h] = 0xffffffffu;
                 if (!slow_brick && sy < ey + 4 && sz < ez + 4 && y >= 0 && y < g.ny && z >= 0 && z < g.nz) {
-                    key0 = ((uint32_t)z * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nx;
-                    g0[h] = a.c.first[key0 + xa];
-                    len[h] = a.c.first[key0 + xb] - g0[h];
-                    if (len[h] == 0) key0 = 0xffffffffu;
+                    rkey[h] = ((uint32_t)z * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nx;
+                    g0[h] = a.c.first[rkey[h] + xa];
+                    len[h] = a.c.first[rkey[h] + xb] - g0[h];
+                    if (len[h] == 0) rkey[h] = 0xffffffffu;
                 }
-                s_rowkey[r] = key0;
+            }
+            // query rows (row = rz * 4 + ry)
+            uint32_t qs = 0, qcnt = 0;
+            {
+                const int ry = lane & 3, rz = lane >> 2;
+                if (lane < kQRows && ry < ey && rz < ez) {
+                    const uint32_t key0 = ((uint32_t)(z0 + rz) * (uint32_t)g.ny + (uint32_t)(y0 + ry)) * (uint32_t)g.nx;
+                    qs = a.q.first[key0 + x0];
+                    qcnt = a.q.first[key0 + x0 + ex] - qs;
+                }
             }
             const uint32_t inc0 = (uint32_t)warp_inclusive_scan((int)len[0], lane);
             const uint32_t tot0 = __shfl_sync(kFull, inc0, 31);
             const uint32_t inc1 = (uint32_t)warp_inclusive_scan((int)len[1], lane) + tot0;
             const uint32_t total = __shfl_sync(kFull, inc1, 31);
             const uint32_t ro[2] = { inc0 - len[0], inc1 - len[1] };
+            const bool staged = !slow_brick && total <= (uint32_t)SLAB;
+            const uint32_t qinc = (uint32_t)warp_inclusive_scan((int)qcnt, lane);
+            const uint32_t nq_all = __shfl_sync(kFull, qinc, 31);
+
+            if (use >= 1) mbar_wait(empty, (use - 1u) & 1u);          // every consumer warp has left the brick that used this buffer
+            s_rowkey[lane] = rkey[0];
+            s_rowkey[lane + 32] = rkey[1];
             s_rowbase[lane] = (int)ro[0] - (int)g0[0];
             s_rowbase[lane + 32] = (int)ro[1] - (int)g0[1];
-            const bool staged = !slow_brick && total <= (uint32_t)SLAB;
-            // ---- query rows (row = rz * 4 + ry)
-            {
-                uint32_t qs = 0, cnt = 0;
-                const int ry = lane & 3, rz = lane >> 2;
-                if (lane < kQRows && ry < ey && rz < ez) {
-                    const uint32_t key0 = ((uint32_t)(z0 + rz) * (uint32_t)g.ny + (uint32_t)(y0 + ry)) * (uint32_t)g.nx;
-                    qs = a.q.first[key0 + x0];
-                    cnt = a.q.first[key0 + x0 + ex] - qs;
-                }
-                const uint32_t inc = (uint32_t)warp_inclusive_scan((int)cnt, lane);
-                const uint32_t nq_all = __shfl_sync(kFull, inc, 31);
-                if (lane < kQRows) { meta[8 + lane] = qs; meta[24 + lane] = inc - cnt; }
-                if (lane == kQRows) meta[24 + lane] = nq_all;
-                if (lane == 0) {
-                    meta[0] = (uint32_t)x0; meta[1] = (uint32_t)y0; meta[2] = (uint32_t)z0; meta[3] = bt.dims;
-                    meta[4] = nq_all; meta[5] = staged ? 1u : 0u; meta[6] = 0u; meta[7] = 0u;
-                }
+            if (lane < kQRows) { meta[8 + lane] = qs; meta[24 + lane] = qinc - qcnt; }
+            if (lane == kQRows) meta[24 + lane] = nq_all;
+            if (lane == 0) {
+                meta[0] = (uint32_t)x0; meta[1] = (uint32_t)y0; meta[2] = (uint32_t)z0; meta[3] = bt.dims;
+                meta[4] = nq_all; meta[5] = staged ? 1u : 0u; meta[6] = 0u; meta[7] = 0u;
             }
             __syncwarp();
             if (lane < kQRows) meta[44 + lane] = (uint32_t)s_rowbase[((lane >> 2) + 2) * kRowPitch + (lane & 3) + 2];
@@ -421,13 +443,13 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
                     }
                 }
                 // T[row][i] = slab position of the first record of cell x0 - 2 + i of that row: one row per load instruction (lane = i),
-                // eight rows in flight
+                // sixteen rows in flight
                 const int n_rows = (ez + 4) * kRowPitch;
                 const int xi0 = min(max(x0 - 2 + lane, 0), g.nx), xi1 = min(max(x0 - 2 + lane + 32, 0), g.nx);
-                for (int r0 = 0; r0 < n_rows; r0 += 8) {
-                    uint32_t v0[8], v1[8];
+                for (int r0 = 0; r0 < n_rows; r0 += 16) {
+                    uint32_t v0[16], v1[16];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
+                    for (int j = 0; j < 16; j++) {
                         const uint32_t key0 = s_rowkey[r0 + j];
                         v0[j] = 0; v1[j] = 0;
                         if (key0 != 0xffffffffu) {
@@ -436,7 +458,7 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
                         }
                     }
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
+                    for (int j = 0; j < 16; j++) {
                         const int r = r0 + j;
                         const bool ok = s_rowkey[r] != 0xffffffffu;
                         const int rb = s_rowbase[r];
@@ -458,6 +480,7 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
         const int query_limit = a.query_limit;
         constexpr uint32_t kDummyOff = (uint32_t)SLAB * 16u;
         unsigned nb_sum = 0, slow_sum = 0;
+        int n_max = 0;
 
         // one brick out of slab buffer B (B is a compile time constant: shared memory addresses fold into the load instructions);
         // returns false when the producer of this buffer has signalled the end of the task list
@@ -482,9 +505,11 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
                 if (wt * 32 >= nq) break;
                 const int ci = wt * 32 + lane;
                 const bool has = ci < nq;
-                int rr = 0;
-#pragma unroll
-                for (int k = 1; k < kQRows; k++) rr += (ci >= (int)meta[24 + k]) ? 1 : 0;
+                // query row of this lane: last row whose first query is <= ci (binary search over the 16 row offsets)
+                int rr = (ci >= (int)meta[24 + 8]) ? 8 : 0;
+                rr += (ci >= (int)meta[24 + rr + 4]) ? 4 : 0;
+                rr += (ci >= (int)meta[24 + rr + 2]) ? 2 : 0;
+                rr += (ci >= (int)meta[24 + rr + 1]) ? 1 : 0;
                 const int ry = rr & 3, rz = rr >> 2;
                 const int qp = has ? (int)meta[8 + rr] + (ci - (int)meta[24 + rr]) : 0;
                 float4 q = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0x7fffffff));
@@ -528,8 +553,8 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
 #pragma unroll
                         for (int dy = 0; dy < 5; dy++) {
                             const float rem = cull - (dy2[dy] + dz2[dz]);
-                            const int i_lo = 2 - ((rem >= ax1) ? 1 : 0) - ((rem >= ax0) ? 1 : 0);
-                            const int i_hi = 3 + ((rem >= ax2) ? 1 : 0) + ((rem >= ax3) ? 1 : 0);
+                            const int i_lo = 2 + fge_mask(rem, ax1) + fge_mask(rem, ax0);
+                            const int i_hi = 3 - fge_mask(rem, ax2) - fge_mask(rem, ax3);
                             const uint16_t* const trow = tq + (dz * kRowPitch + dy) * kTW;
                             uint32_t lo = trow[i_lo];
                             const uint32_t hi = trow[i_hi];
@@ -571,10 +596,8 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
                     uint32_t p = w & 0xffffu, e = w >> 16;
                     uint32_t wn = lds_u32(tab_a + 128);
                     uint32_t rp = tab_a + 256;
-                    float4 c = lds_f4(slab_a + p);
-#pragma unroll 4
-                    for (int it = 0; it < maxtot; it++) {
-                        const uint32_t pc = p;
+                    // candidates are loaded two iterations ahead of their test
+                    auto advance = [&]() {
                         p += 16u;
                         if (p == e) {
                             p = wn & 0xffffu;
@@ -582,19 +605,32 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
                             wn = lds_u32(rp);
                             rp += 128u;
                         }
+                    };
+                    uint32_t pc0 = p;
+                    float4 c0 = lds_f4(slab_a + p);
+                    advance();
+                    uint32_t pc1 = p;
+                    float4 c1 = lds_f4(slab_a + p);
+                    advance();
+#pragma unroll 6
+                    for (int it = 0; it < maxtot; it++) {
+                        const uint32_t pn = p;
                         const float4 cn = lds_f4(slab_a + p);
-                        const float d2 = dist2(q.x, q.y, q.z, c.x, c.y, c.z);
+                        advance();
+                        const float d2 = dist2(q.x, q.y, q.z, c0.x, c0.y, c0.z);
                         bool hit = d2 <= r2;
-                        if (SYMMETRIC) hit = hit || (d2 <= lds_f32(buf_a + SM::kOffR2 + (pc >> 2)));
+                        if (SYMMETRIC) hit = hit || (d2 <= lds_f32(buf_a + SM::kOffR2 + (pc0 >> 2)));
                         if (hit) {
-                            sts_u16(ca, pc);
+                            sts_u16(ca, pc0);
                             ca = min(ca + (uint32_t)kColStride, col_cap);
                         }
-                        c = cn;
+                        c0 = c1; pc0 = pc1;
+                        c1 = cn; pc1 = pn;
                     }
                     if (active && !slow && ca == col_cap) slow = true;          // the column is full: the list may be longer
                 }
                 const int n = (int)((ca - col_a) / (uint32_t)kColStride);
+                n_max = max(n_max, n);
 
                 // ---- publish the 32 lists: [n, j0, j1, ...] back to back, one reservation per warp
                 const bool valid = active && !slow;
@@ -614,25 +650,35 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
                         // table instead of shuffles; one coalesced store per 32 list words
                         sts_u32(tab_a, (uint32_t)words | ((uint32_t)off << 8));
                         __syncwarp();
-                        int32_t* const out_l = a.ragged + base + lane;
+                        const int32_t* const out_l = a.ragged + base + lane;
                         const uint32_t id_a = slab_a + 12u;
                         const uint32_t tab_w = tab_a - (uint32_t)lane * 4u;
                         uint32_t colk = col_w + (uint32_t)lane * kColStride - kColStride;       // entry (lane - 1) of column k
 #pragma unroll 1
-                        for (int k = 0; k < 32; k++, colk += 2u) {
-                            const uint32_t wo = lds_u32(tab_w + (uint32_t)k * 4u);
-                            const int wk = (int)(wo & 0xffu);
-                            int32_t* const o = out_l + (wo >> 8);
-                            if (lane < wk) {
-                                int v = wk - 1;
-                                if (lane > 0) v = (int)lds_u32(id_a + lds_u16(colk));
-                                __stcs(o, v);
+                        for (int k0 = 0; k0 < 32; k0 += 4, colk += 8u) {
+                            // four lists per round: all shared memory loads first, then the stores
+                            uint32_t wo[4];
+                            int v0[4], v1[4];
+#pragma unroll
+                            for (int j = 0; j < 4; j++) wo[j] = lds_u32(tab_w + (uint32_t)(k0 + j) * 4u);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const int wk = (int)(wo[j] & 0xffu);
+                                v0[j] = wk - 1;
+                                v1[j] = 0;
+                                if (lane > 0 && lane < wk) v0[j] = (int)lds_u32(id_a + lds_u16(colk + 2u * j));
+                                if (lane + 32 < wk) v1[j] = (int)lds_u32(id_a + lds_u16(colk + 2u * j + 32u * kColStride));
                             }
-                            if (lane + 32 < wk) __stcs(o + 32, (int)lds_u32(id_a + lds_u16(colk + 32u * kColStride)));
-                            if (KMAX > 63) {
-                                if (wk > 64) {
-                                    for (int u = lane + 64; u < wk; u += 32)
-                                        __stcs(o + (u - lane), (int)lds_u32(id_a + lds_u16(colk + (uint32_t)(u - lane) * kColStride)));
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const int wk = (int)(wo[j] & 0xffu);
+                                if (lane < wk) stg_cs_at(out_l, wo[j] >> 8, v0[j]);
+                                if (lane + 32 < wk) stg_cs_at32(out_l, wo[j] >> 8, v1[j]);
+                                if (KMAX > 63) {
+                                    if (wk > 64) {
+                                        for (int u = lane + 64; u < wk; u += 32)
+                                            stg_cs_at(out_l, (wo[j] >> 8) + (uint32_t)(u - lane), (int)lds_u32(id_a + lds_u16(colk + 2u * j + (uint32_t)(u - lane) * kColStride)));
+                                    }
                                 }
                             }
                         }
@@ -671,6 +717,8 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
             if (nb_sum) atomicAdd(a.n_neighbors, (unsigned long long)nb_sum);
             if (slow_sum) atomicAdd(a.n_slow, (unsigned long long)slow_sum);
         }
+        n_max = __reduce_max_sync(kFull, n_max);
+        if (lane == 0 && n_max > 0) atomicMax(a.max_list, n_max);
     }
 }
 

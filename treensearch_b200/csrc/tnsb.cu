@@ -74,6 +74,8 @@ struct PairCounters {
     uint32_t n_tasks;
     int plan_overflow;
     unsigned long long n_slow;
+    int max_list;
+    int pad_;
 };
 
 struct SetState {
@@ -159,7 +161,7 @@ struct tnsb_context {
     int opt_bucket_passes = 0;          // 0: automatic
     int opt_build = 0;             // 0: bucket build when the cell table is small enough, else radix sort; 1: always radix sort
     int opt_query_kernel = 0;      // 0: automatic (brick query on the half-radius grid while its cell table is affordable, else the cell kernel), 1: always the cell kernel
-    int brick_kmax = 64;           // hit column height of the brick query; raised (sticky) when too many queries overflow it
+    int brick_kmax = 128;          // hit column height of the brick query: 128 on the first run, then 64 while the longest list of the previous run fits
 
     // world box with hysteresis (TreeNSearch.cpp:474-482)
     bool domain_valid = false;
@@ -583,6 +585,7 @@ int query_pair_brick(tnsb_context* c, int si, int sj, PairCounters* d_cnt)
     a.cursor = &d_cnt->cursor;
     a.n_neighbors = &d_cnt->n_neighbors;
     a.n_slow = &d_cnt->n_slow;
+    a.max_list = &d_cnt->max_list;
     a.overflow = &d_cnt->overflow;
     cudaStream_t s = c->stream;
     brick_plan_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(n_bricks, 8), 8 * c->n_sms), 256, 0, s>>>(bg, a.q.first, a.c.first, slab_cap, a.tasks, a.max_tasks, a.n_tasks, a.plan_overflow);
@@ -787,6 +790,7 @@ int run_impl(tnsb_context* c)
     PairCounters* h_out = h_init + std::max<size_t>(n_pairs, 1);
     const int qlimit = c->opt_query_limit >= 0 ? (int)std::min<int64_t>(c->opt_query_limit, INT_MAX) : INT_MAX;
 
+    int brick_max_list = 0;
     std::vector<int> todo;
     for (int id : act) {
         const int si = id / n_sets;
@@ -832,6 +836,7 @@ int run_impl(tnsb_context* c)
             PairState& ps = c->pairs[id];
             const PairCounters& r = h_out[id];
             c->stats.n_slow_queries += (int64_t)r.n_slow;
+            brick_max_list = std::max(brick_max_list, r.n_slow > 0 ? 1000 : r.max_list);
             if (r.plan_overflow) {
                 // the planner kept counting: n_tasks is the exact number of bricks
                 ps.max_tasks = (int64_t)r.n_tasks + 1024;
@@ -857,8 +862,8 @@ int run_impl(tnsb_context* c)
         }
         todo.swap(again);
     }
-    // lists longer than the brick query's hit columns went through its slow path: use the tall columns from the next run on
-    if (c->brick_mode && c->brick_kmax == 64 && c->stats.n_slow_queries * 50 > std::max<int64_t>(n_total, 1)) c->brick_kmax = 128;
+    // hit column height of the next run: the short columns (more warps per SM) while the longest list leaves some headroom
+    if (c->brick_mode && !act.empty()) c->brick_kmax = brick_max_list <= 62 ? 64 : 128;
     if (c->opt_sort_lists) {
         for (int id : act) {
             PairState& ps = c->pairs[id];
