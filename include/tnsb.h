@@ -166,12 +166,17 @@ int tnsb_get_neighborlists_device(const tnsb_context* ctx, int set_i, int set_j,
                                   const int32_t** d_ragged, const int64_t** d_list_pos, int64_t* n_ints);
 
 /* replaces: prepare_zsort()     TreeNSearch.h:202 / .cpp:2571-2716.  new -> old permutation per set by Morton key of the grid cell
-   (x lowest bit, libmorton order), stable inside a cell. */
+   (x lowest bit, libmorton order), stable inside a cell.  After a tnsb_run() whose grid is still valid (no resize since) the order
+   comes from the records resident in HBM (no upload, like the reference's reuse of its cells, :2598-2661). */
 int tnsb_prepare_zsort(tnsb_context* ctx);
 /* replaces: get_zsort_order(set) TreeNSearch.h:334 / .cpp:250-253 */
 int tnsb_get_zsort_order(const tnsb_context* ctx, int set_i, const int32_t** new_to_old, int* n_points);
-/* device-side apply_zsort for float32 arrays resident in HBM: data[new*stride + c] = tmp[old*stride + c]
-   (host arrays of arbitrary T are gathered by the header template, TreeNSearch.h:443-481) */
+/* replaces: apply_zsort<T>(set_i, T*, stride)  TreeNSearch.h:443-481, for arrays resident in HBM: ONE launch gathers up to 8 arrays of
+   set_i (positions, velocities, ...): dst_k[new] = src_k[old], rows of row_bytes[k] bytes (a multiple of 4: any T / stride the
+   reference's template takes).  dst_k == src_k permutes in place through an internal staging copy, like the reference does.
+   (host arrays of arbitrary T are gathered by the header template) */
+int tnsb_apply_zsort_device(tnsb_context* ctx, int set_i, int n_arrays, const void* const* d_src, void* const* d_dst, const int* row_bytes);
+/* the same for one float32 array in place: data[new*stride + c] = tmp[old*stride + c] */
 int tnsb_apply_zsort_device_f32(tnsb_context* ctx, int set_i, float* d_data, int stride);
 
 /* ---- multi-GPU: Z-slab decomposition helpers (no counterpart in the single-process reference) ---------------- */

@@ -190,25 +190,49 @@ def test_c2_10m_uniform(tnsb):
     assert np.array_equal(d1, loader.list_digests(ragged, pos + 1, ragged[pos]))
 
 
-def test_c3_dam_break_with_zsort(tnsb):
-    n = 2_000_000
+def _c3_loop(tnsb, n, n_steps, zsort_every, check_steps, use_reference):
+    """BASELINE config 3: dam-break cloud, prepare_zsort + apply_zsort before step 0 and every `zsort_every` steps, points advected
+    by <= 0.1 d per step; digests of all lists against the reference / the port on `check_steps`, neighbour totals on
+    every step."""
     pts, d, r = clouds.dam_break_cloud(n)
     pts = pts.copy()
     eng = tnsb.TreeNSearch()
     eng.set_search_radius(float(r))
     eng.add_point_set(pts)
     eng.set_active_search(0, 0, True)
-    for step in range(3):
-        if step % 2 == 0:
+    for step in range(n_steps):
+        if step % zsort_every == 0:
             eng.prepare_zsort()
             eng.apply_zsort(0, pts, 3)
         eng.run()
-        case = dict(sets=[(pts, None)], radius=float(r), pairs=[(0, 0)], symmetric=True)
-        port = cases.configure(loader.OraclePort(), case)
-        port.run(1)
-        _digest_compare(eng, (0, 0), *port.csr(0, 0))
+        if step in check_steps:
+            case = dict(sets=[(pts, None)], radius=float(r), pairs=[(0, 0)], symmetric=True)
+            if use_reference:
+                ref = cases.configure(loader.Reference(), case)
+                ref.run(0)
+                _digest_compare(eng, (0, 0), *ref.csr(0, 0, sort_lists=False))
+                assert ref.pair_total(0, 0) == eng.stats()["n_neighbors"]
+                ref.close()
+            else:
+                port = cases.configure(loader.OraclePort(), case)
+                port.run(1)
+                _digest_compare(eng, (0, 0), *port.csr(0, 0))
+                port.close()
         pts[...] = clouds.advect(pts, d, step)
     assert eng.stats()["n_neighbors"] / n > 40
+    return eng
+
+
+def test_c3_dam_break_with_zsort(tnsb):
+    _c3_loop(tnsb, 2_000_000, 3, 2, (0, 1, 2), use_reference=False)
+
+
+def test_c3_10m_dam_break_zsort_every_10_vs_reference(tnsb):
+    """Config 3 at its stated size: 10M points, 20 steps, zsort before steps 0 and 10, against the unmodified reference."""
+    if not loader.reference_available():
+        pytest.skip("oracle/_ref not present")
+    eng = _c3_loop(tnsb, 10_000_000, 20, 10, (0, 9, 10, 19), use_reference=True)
+    assert eng.stats()["brick_query"] == 1
 
 
 def test_c4_two_sets_variable_radii(tnsb):
@@ -220,6 +244,22 @@ def test_c4_two_sets_variable_radii(tnsb):
         port.run(1)
         for p in case["pairs"]:
             _digest_compare(eng, p, *port.csr(*p))
+
+
+@pytest.mark.parametrize("sym", [True, False])
+def test_c4_2m_500k_vs_reference(tnsb, sym):
+    """Config 4 at its stated size: 2M fluid + 500K boundary points, per-point radii, searches 0->0, 0->1, 1->0, against the reference."""
+    if not loader.reference_available():
+        pytest.skip("oracle/_ref not present")
+    p0, r0, p1, r1, _ = clouds.two_set_cloud(2_000_000, 500_000)
+    case = dict(sets=[(p0, r0), (p1, r1)], radius=None, pairs=[(0, 0), (0, 1), (1, 0)], symmetric=sym)
+    eng = run_engine(tnsb, case)
+    eng.run()                                       # second run: column height picked from the first run's longest list
+    ref = cases.configure(loader.Reference(), case)
+    ref.run(0)
+    for p in case["pairs"]:
+        _digest_compare(eng, p, *ref.csr(*p, sort_lists=False))
+    assert not eng.is_search_active(1, 1)
 
 
 # ---------------------------------------------------------------------------------------------------- engine behaviour
@@ -407,6 +447,127 @@ def test_set_active_search_overloads(tnsb):
     eng.set_all_searches(True)
     assert all(eng.is_search_active(i, j) for i in range(3) for j in range(3))
     assert eng.does_set_exist(2) and not eng.does_set_exist(3)
+
+
+def test_device_apply_zsort_matches_host(tnsb):
+    """tnsb_apply_zsort_device: fused gather of several resident arrays (float32 xyz, float64 velocity, int32 tag) in one launch,
+    in place and out of place, against the host apply_zsort (TreeNSearch.h:443-481)."""
+    import torch
+    n = 60_000
+    pts = clouds.uniform_cloud(n, 23).copy()
+    vel = np.random.RandomState(1).standard_normal((n, 3))
+    tag = np.arange(n, dtype=np.int32)
+    eng = tnsb.TreeNSearch()
+    eng.set_search_radius(float(clouds.radius_for_mean_neighbors(n)))
+    d_pts = torch.from_numpy(pts).cuda()
+    eng.add_point_set(d_pts)
+    eng.set_active_search(0, 0, True)
+    eng.run()
+    eng.prepare_zsort()                     # grid of the last run is valid: order from the resident records, no upload
+    assert eng.stats()["h2d_bytes"] == 0
+    order = eng.get_zsort_order(0).copy()
+    assert np.array_equal(np.sort(order), np.arange(n))
+    d_vel, d_tag = torch.from_numpy(vel).cuda(), torch.from_numpy(tag).cuda()
+    out_tag = torch.empty_like(d_tag)
+    eng.apply_zsort_device(0, [d_pts, d_vel], [3, 3])            # in place, two arrays, one launch
+    eng.apply_zsort_device(0, [d_tag], [1], out=[out_tag])       # out of place
+    assert np.array_equal(d_pts.cpu().numpy(), pts[order])
+    assert np.array_equal(d_vel.cpu().numpy(), vel[order])
+    assert np.array_equal(out_tag.cpu().numpy(), order) and np.array_equal(d_tag.cpu().numpy(), tag)
+    # the single-array float32 entry point and the host template agree
+    d2 = torch.from_numpy(pts).cuda()
+    eng.apply_zsort(0, d2, 3)
+    host = pts.copy()
+    eng.apply_zsort(0, host, 3)
+    assert np.array_equal(d2.cpu().numpy(), host) and np.array_equal(host, pts[order])
+    # searching the permuted points gives the same sets (renumbered)
+    eng.run()
+    case = dict(sets=[(host, None)], radius=float(clouds.radius_for_mean_neighbors(n)), pairs=[(0, 0)], symmetric=True)
+    assert_matches_port(eng, case)
+
+
+def test_zsort_reuses_resident_grid_same_order(tnsb):
+    """prepare_zsort() after run() (resident records) hands out the same permutation as prepare_zsort() from scratch."""
+    n = 80_000
+    pts, d, r = clouds.dam_break_cloud(n)
+    a = tnsb.TreeNSearch()
+    a.set_search_radius(float(r)); a.add_point_set(pts); a.set_active_search(0, 0, True)
+    a.prepare_zsort()
+    scratch = a.get_zsort_order(0).copy()
+    b = tnsb.TreeNSearch()
+    b.set_search_radius(float(r)); b.add_point_set(pts); b.set_active_search(0, 0, True)
+    b.run()
+    b.prepare_zsort()
+    assert np.array_equal(b.get_zsort_order(0), scratch)
+
+
+def test_pin_user_memory_option(tnsb):
+    """TNSB_OPT_PIN_USER_MEMORY: pageable user arrays are registered once and re-read on every run (the engine borrows them)."""
+    case = cases.GOLDEN_CASES["uniform_fixed_5000"]()
+    pts = case["sets"][0][0].copy()
+    eng = tnsb.TreeNSearch()
+    eng.set_option(tnsb.TNSB_OPT_PIN_USER_MEMORY, 1)
+    eng.set_search_radius(case["radius"])
+    eng.add_point_set(pts)
+    eng.set_active_search(0, 0, True)
+    eng.run()
+    assert_matches_port(eng, case)
+    pts[:, 0] = pts[::-1, 0].copy()                 # the user mutates the borrowed array in place
+    eng.run()
+    assert_matches_port(eng, dict(case, sets=[(pts, None)]))
+    assert eng.stats()["h2d_bytes"] == pts.nbytes
+
+
+def test_print_state_and_stats(tnsb, capsys):
+    case = cases.GOLDEN_CASES["variable_random_sym"]()
+    eng = run_engine(tnsb, case)
+    eng.print_state()
+    out = capsys.readouterr().out
+    assert "NEIGHBORLISTS" in out and "set_0 -> set_1" in out and "n_neighbors set_1 -> set_0 [min, max, avg]" in out
+    port = cases.configure(loader.OraclePort(), case)
+    port.run(1)
+    off, _ = port.csr(0, 0)
+    cnt = np.diff(off)
+    line = [l for l in out.splitlines() if l.startswith("n_neighbors set_0 -> set_0")][0]
+    assert f"[{cnt.min()}, {cnt.max()}," in line
+
+
+def test_cell_size_semantics(tnsb):
+    """set_cell_size (TreeNSearch.cpp:173-181, :300, :368): any positive value is accepted once and does not change the results; exactly 0
+    is the reference's "cell_size is not set" error at run(); a negative value means "use the default"."""
+    case = cases.GOLDEN_CASES["uniform_fixed_5000"]()
+    for cs in (0.5 * case["radius"], 3.0 * case["radius"], -1.0):
+        eng = tnsb.TreeNSearch()
+        eng.set_cell_size(cs)
+        eng.set_search_radius(case["radius"])
+        eng.add_point_set(case["sets"][0][0])
+        eng.set_active_search(0, 0, True)
+        eng.run()
+        assert_matches_port(eng, case)
+    eng = tnsb.TreeNSearch()
+    eng.set_cell_size(0.0)
+    eng.set_search_radius(case["radius"])
+    eng.add_point_set(case["sets"][0][0])
+    with pytest.raises(tnsb.TreeNSearchError, match="cell_size is not set"):
+        eng.run()
+
+
+def test_resize_fast_path_keeps_grid(tnsb):
+    """resize_point_set with the same pointer and size is a no-op (TreeNSearch.cpp:77-79, :107-109): the grid stays valid for prepare_zsort."""
+    import torch
+    case = cases.GOLDEN_CASES["uniform_fixed_5000"]()
+    pts = torch.from_numpy(case["sets"][0][0]).cuda()
+    eng = tnsb.TreeNSearch()
+    eng.set_search_radius(case["radius"])
+    eng.add_point_set(pts)
+    eng.set_active_search(0, 0, True)
+    eng.run()
+    launches = eng.stats()["n_kernel_launches"]
+    eng.resize_point_set(0, pts)
+    eng.prepare_zsort()                              # still the resident grid: far fewer launches than a build from scratch
+    assert eng.stats()["n_kernel_launches"] == launches
+    eng.run()
+    assert_matches_port(eng, case)
 
 
 # ---------------------------------------------------------------------------------------------------- the cell kernel (option 1)

@@ -82,6 +82,7 @@ SIGNATURES = {
     "tnsb_get_neighborlists_device": (C.c_int, [_vp, C.c_int, C.c_int, _i32pp, _i64pp, C.POINTER(C.c_int64)]),
     "tnsb_prepare_zsort": (C.c_int, [_vp]),
     "tnsb_get_zsort_order": (C.c_int, [_vp, C.c_int, _i32pp, C.POINTER(C.c_int)]),
+    "tnsb_apply_zsort_device": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int)]),
     "tnsb_apply_zsort_device_f32": (C.c_int, [_vp, C.c_int, _vp, C.c_int]),
     "tnsb_shard_aabb": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "tnsb_shard_histogram": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, _vp]),

@@ -46,6 +46,14 @@ def _as_buffer(a, dtypes, what):
     return a.ctypes.data, a.size, a.dtype == np.float64, a
 
 
+class _EngineView(np.ndarray):
+    """numpy view of engine-owned memory that holds a reference to its engine (so the buffers outlive the view)."""
+    _owner = None
+
+    def __array_finalize__(self, obj):
+        self._owner = getattr(obj, "_owner", None)
+
+
 class NeighborList:
     """Handle to one neighbour list (reference: TreeNSearch/source/NeighborList.h:8-39)."""
     __slots__ = ("_view",)
@@ -154,6 +162,12 @@ class TreeNSearch:
                 n_i = min(n_i, self._query_limit)      # find-only (halo) points have no list
             ragged = np.ctypeslib.as_array(rag, shape=(max(n_ints.value, 1),))[: n_ints.value] if n_ints.value > 0 else np.zeros(0, np.int32)
             list_pos = np.ctypeslib.as_array(pos, shape=(max(n_i, 1),))[:n_i] if n_i > 0 else np.zeros(0, np.int64)
+            # zero-copy views of engine-owned pinned memory: they keep the engine alive, are read-only, and -- exactly like the
+            # reference's NeighborList pointers (TreeNSearch.cpp:393) -- are invalidated by the next run() / close()
+            ragged, list_pos = ragged.view(_EngineView), list_pos.view(_EngineView)
+            ragged._owner = list_pos._owner = self
+            ragged.flags.writeable = False
+            list_pos.flags.writeable = False
             v = (ragged, list_pos)
             self._views[key] = v
         return v
@@ -181,12 +195,9 @@ class TreeNSearch:
 
     def apply_zsort(self, set_i, data, stride=1):
         """In-place gather data[new] = data[old] (TreeNSearch.h:443-481).  numpy arrays are gathered on the host;
-        float32 torch CUDA tensors on the device."""
+        torch CUDA tensors (any dtype whose rows are a multiple of 4 bytes) on the device."""
         if _is_torch(data) and data.is_cuda:
-            import torch
-            if data.dtype != torch.float32 or not data.is_contiguous():
-                raise TypeError("device apply_zsort needs a contiguous float32 tensor")
-            self._check(self._lib.tnsb_apply_zsort_device_f32(self._h, int(set_i), data.data_ptr(), int(stride)))
+            self.apply_zsort_device(set_i, [data], [stride])
             return
         order = self.get_zsort_order(set_i)
         if _is_torch(data):
@@ -195,6 +206,29 @@ class TreeNSearch:
         flat = data.reshape(-1)
         rows = flat[: n * stride].reshape(n, stride)
         rows[...] = rows[order.astype(np.int64)]
+
+    def apply_zsort_device(self, set_i, arrays, strides=None, out=None):
+        """Fused device gather of several per-point arrays of set_i in ONE launch (positions, velocities, ...):
+        arrays[k][new] = arrays[k][old] in place, or into out[k] when given.  arrays: contiguous torch CUDA tensors;
+        strides[k] = elements per point (default: inferred from the tensor shape)."""
+        n = self.get_n_points_in_set(set_i)
+        k = len(arrays)
+        src = (C.c_void_p * k)()
+        dst = (C.c_void_p * k)()
+        row = (C.c_int * k)()
+        for i, a in enumerate(arrays):
+            if not (_is_torch(a) and a.is_cuda and a.is_contiguous()):
+                raise TypeError("apply_zsort_device needs contiguous torch CUDA tensors")
+            stride = int(strides[i]) if strides is not None else (a.numel() // max(n, 1))
+            if a.numel() < n * stride:
+                raise ValueError("array shorter than n_points * stride")
+            src[i] = a.data_ptr()
+            o = a if out is None else out[i]
+            if o is not a and not (_is_torch(o) and o.is_cuda and o.is_contiguous() and o.numel() >= n * stride and o.element_size() == a.element_size()):
+                raise TypeError("out[k] must be a contiguous CUDA tensor shaped like arrays[k]")
+            dst[i] = o.data_ptr()
+            row[i] = stride * a.element_size()
+        self._check(self._lib.tnsb_apply_zsort_device(self._h, int(set_i), k, src, dst, row))
 
     def set_symmetric_search(self, activate):
         self._check(self._lib.tnsb_set_symmetric_search(self._h, int(bool(activate))))

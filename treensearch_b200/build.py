@@ -41,5 +41,21 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+BENCH_CPP_SRC = os.path.join(_HERE, "..", "tools", "bench_cpp.cpp")
+BENCH_CPP = os.path.join(_HERE, "bench_cpp")
+
+
+def build_bench_cpp(force: bool = False) -> str:
+    """tools/bench_cpp.cpp against include/TreeNSearch + libtnsb.so: the drop-in C++ caller bench.py times end to end."""
+    build_library()
+    if not force and os.path.exists(BENCH_CPP) and os.path.getmtime(BENCH_CPP) > max(os.path.getmtime(BENCH_CPP_SRC), os.path.getmtime(OUT)):
+        return BENCH_CPP
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [gxx, "-O2", "-std=c++17", "-I", os.path.join(_HERE, "..", "include"), BENCH_CPP_SRC, "-o", BENCH_CPP,
+           "-L", _HERE, "-ltnsb", "-Wl,-rpath,$ORIGIN"]
+    subprocess.run(cmd, check=True)
+    return BENCH_CPP
+
+
 if __name__ == "__main__":
     print(build_library(force=True, verbose=True))

@@ -328,6 +328,42 @@ __global__ void __launch_bounds__(256) cell_population_kernel(const Key* __restr
     table[cell_key[c]] = cell_start[c + 1] - cell_start[c];
 }
 
+// prepare_zsort() on top of a resident grid: Morton key (cell = r grid, libmorton order) of every SORTED record, written at the
+// record's original index, so that a stable radix sort of (key, index) yields the same order as a build from the raw arrays
+template <typename Key>
+__global__ void __launch_bounds__(256) zsort_keys_kernel(const float4* __restrict__ sorted, int n, GridParams g, Key* __restrict__ keys_by_index)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 v = sorted[i];
+    int cx = __double2int_rd(((double)v.x - g.bottom[0]) * g.inv_cell);
+    int cy = __double2int_rd(((double)v.y - g.bottom[1]) * g.inv_cell);
+    int cz = __double2int_rd(((double)v.z - g.bottom[2]) * g.inv_cell);
+    cx = min(max(cx, 0), g.max_coord);
+    cy = min(max(cy, 0), g.max_coord);
+    cz = min(max(cz, 0), g.max_coord);
+    keys_by_index[__float_as_int(v.w)] = Morton<Key>::encode((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+}
+
+// fused multi-array gather of apply_zsort on the device: dst_k[row] = src_k[new_to_old[row]] for up to 8 arrays of 4-byte words
+constexpr int kMaxZsortArrays = 8;
+struct ZsortArrays {
+    const uint32_t* src[kMaxZsortArrays];
+    uint32_t* dst[kMaxZsortArrays];
+    int row_words[kMaxZsortArrays];
+    int n_arrays;
+};
+__global__ void __launch_bounds__(256) gather_arrays_kernel(ZsortArrays a, const int32_t* __restrict__ new_to_old, int n)
+{
+    const int k = blockIdx.y;
+    const int w = a.row_words[k];
+    const int64_t total = (int64_t)n * w;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(t / w), c = (int)(t - (int64_t)row * w);
+        a.dst[k][t] = a.src[k][(int64_t)new_to_old[row] * w + c];
+    }
+}
+
 // gather used by tnsb_apply_zsort_device_f32
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, const int32_t* __restrict__ new_to_old,
                                                           int n, int stride)

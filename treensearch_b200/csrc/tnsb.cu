@@ -208,6 +208,19 @@ int fail(tnsb_context* c, int code, const std::string& msg)
         }                                                                                                    \
     } while (0)
 
+// makes the context's device current for one entry point and restores the caller's device on every exit path
+struct DeviceGuard {
+    int prev = -1, dev;
+    explicit DeviceGuard(int d) : dev(d)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 bool is_device_pointer(const void* p)
 {
     if (!p) return false;
@@ -245,7 +258,9 @@ int stage_input(tnsb_context* c, const void* src, size_t bytes, DevBuf& up, cons
 
 int validate(tnsb_context* c)
 {
-    // TreeNSearch::_check(), TreeNSearch.cpp:366-392
+    // TreeNSearch::_check(), TreeNSearch.cpp:366-392.  A cell size of exactly 0 is the one value the reference neither replaces by its
+    // default (that needs < 0, :300) nor accepts (:368); this engine's grid does not depend on the value otherwise.
+    if (c->user_cell_size == 0.0f) return fail(c, TNSB_ERR_INVALID_STATE, "TreeNSearch error: cell_size is not set. Use TreeNSearch::set_cell_size().");
     if (c->radius_set && c->radius <= 0.0f) return fail(c, TNSB_ERR_INVALID_STATE, "TreeNSearch error: global_search_radius <= 0.");
     if (c->radius_set && c->n_sets_with_radii > 0)
         return fail(c, TNSB_ERR_INVALID_STATE, "TreeNSearch error: global search radius and per-point variable search radii specified.");
@@ -606,6 +621,35 @@ int query_pair_brick(tnsb_context* c, int si, int sj, PairCounters* d_cnt)
     return TNSB_OK;
 }
 
+// prepare_zsort() when the grid of the last run() is still valid (the reference reuses its cells, TreeNSearch.cpp:2598-2661): the
+// sorted records are resident, so no upload, no world box, no bucket build -- only Morton keys of the records and the radix sort
+template <typename Key>
+int zsort_from_grid(tnsb_context* c)
+{
+    cudaStream_t s = c->stream;
+    GridParams gp;
+    for (int d = 0; d < 3; d++) gp.bottom[d] = c->dom_bottom[d];
+    gp.inv_cell = 1.0 / c->cell;
+    gp.bits = c->bits;
+    gp.max_coord = (int)((1ll << c->bits) - 1);
+    int launches = 0, passes = 0;
+    for (auto& st : c->sets) {
+        if (st.n == 0) continue;
+        for (int b = 0; b < 2; b++) {
+            TNSB_CUDA(c, st.keys[b].ensure(sizeof(Key) * (size_t)st.n, 1.1));
+            TNSB_CUDA(c, st.vals[b].ensure(sizeof(uint32_t) * (size_t)st.n, 1.1));
+        }
+        zsort_keys_kernel<Key><<<ceil_div(st.n, 256), 256, 0, s>>>(st.sorted.as<float4>(), st.n, gp, st.keys[0].as<Key>());
+        TNSB_CUDA(c, c->sort_temp.ensure(sizeof(uint32_t) * (size_t)radix_sort_temp_elems<Key>(st.n), 1.1));
+        Key* keys[2] = { st.keys[0].as<Key>(), st.keys[1].as<Key>() };
+        uint32_t* vals[2] = { st.vals[0].as<uint32_t>(), st.vals[1].as<uint32_t>() };
+        st.sel = radix_sort_pairs<Key>(keys, vals, st.n, 3 * c->bits, c->sort_temp.as<uint32_t>(), s, &launches, &passes);
+        st.order_valid = true;
+    }
+    TNSB_CUDA(c, cudaGetLastError());
+    return TNSB_OK;
+}
+
 double ms_since(const std::chrono::steady_clock::time_point& t0)
 {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -758,7 +802,7 @@ int run_impl(tnsb_context* c)
     const auto t0 = std::chrono::steady_clock::now();
     int rc = validate(c);
     if (rc != TNSB_OK) return rc;
-    TNSB_CUDA(c, cudaSetDevice(c->device));
+    DeviceGuard device_guard(c->device);
     memset(&c->stats, 0, sizeof(c->stats));
     const int n_sets = (int)c->sets.size();
     if (n_sets > 64) return fail(c, TNSB_ERR_LIMIT, "tnsb: at most 64 point sets are supported.");
@@ -977,7 +1021,7 @@ int tnsb_create(tnsb_context** out, int device)
 void tnsb_destroy(tnsb_context* c)
 {
     if (!c) return;
-    cudaSetDevice(c->device);
+    DeviceGuard device_guard(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->registered) cudaHostUnregister(const_cast<void*>(kv.first));
     for (auto& st : c->sets) {
@@ -1041,6 +1085,8 @@ int tnsb_resize_point_set_f32(tnsb_context* c, int s, const float* pts, const fl
     int rc = resize_common(c, s, n, variable_radius != 0);
     if (rc != TNSB_OK) return rc;
     auto& st = c->sets[s];
+    // same pointers, same size: nothing changes, the grid of the last run stays valid for prepare_zsort() (TreeNSearch.cpp:77-79, :107-109)
+    if (!st.is_f64 && st.u_pts_f32 == pts && st.n == n && (!variable_radius || st.u_radii_f32 == radii)) return TNSB_OK;
     st.u_pts_f32 = pts; st.u_pts_f64 = nullptr;
     if (variable_radius) { st.u_radii_f32 = radii; st.u_radii_f64 = nullptr; }
     else if (st.is_f64) { st.u_radii_f32 = nullptr; st.u_radii_f64 = nullptr; }
@@ -1055,6 +1101,7 @@ int tnsb_resize_point_set_f64(tnsb_context* c, int s, const double* pts, const d
     int rc = resize_common(c, s, n, variable_radius != 0);
     if (rc != TNSB_OK) return rc;
     auto& st = c->sets[s];
+    if (st.is_f64 && st.u_pts_f64 == pts && st.n == n && (!variable_radius || st.u_radii_f64 == radii)) return TNSB_OK;     // TreeNSearch.cpp:88-90, :124-126
     st.u_pts_f64 = pts; st.u_pts_f32 = nullptr;
     if (variable_radius) { st.u_radii_f64 = radii; st.u_radii_f32 = nullptr; }
     else if (!st.is_f64) { st.u_radii_f32 = nullptr; st.u_radii_f64 = nullptr; }
@@ -1213,11 +1260,19 @@ int tnsb_prepare_zsort(tnsb_context* c)
     if (!c) return TNSB_ERR_INVALID_ARGUMENT;
     int rc = validate(c);
     if (rc != TNSB_OK) return rc;
-    TNSB_CUDA(c, cudaSetDevice(c->device));
-    bool all_valid = true;
+    DeviceGuard device_guard(c->device);
+    bool all_valid = true, all_resident = c->domain_valid;
     int64_t n_total = 0;
-    for (auto& st : c->sets) { all_valid = all_valid && ((st.sorted_valid && st.order_valid) || st.n == 0); n_total += st.n; }
-    if ((!all_valid || c->brick_mode) && n_total > 0) {
+    for (auto& st : c->sets) {
+        all_valid = all_valid && ((st.sorted_valid && st.order_valid) || st.n == 0);
+        all_resident = all_resident && (st.sorted_valid || st.n == 0);
+        n_total += st.n;
+    }
+    if (n_total > 0 && all_resident && (!all_valid || c->brick_mode)) {
+        // the grid of the last run is valid but carries no stable Morton permutation (bucket / brick build): Z-order of the resident records
+        rc = c->key64 ? zsort_from_grid<uint64_t>(c) : zsort_from_grid<uint32_t>(c);
+        if (rc != TNSB_OK) return rc;
+    } else if ((!all_valid || c->brick_mode) && n_total > 0) {
         // no grid of the current points yet (TreeNSearch.cpp:2592-2595), or a grid without a stable Morton permutation (bucket build,
         // row-key order): the order handed to the user is the libmorton Z-order, stable inside a cell, so radix sort by Morton keys now
         GridParams gp;
@@ -1251,30 +1306,64 @@ int tnsb_get_zsort_order(const tnsb_context* c, int s, const int32_t** new_to_ol
     return TNSB_OK;
 }
 
-int tnsb_apply_zsort_device_f32(tnsb_context* c, int s, float* d_data, int stride)
+int tnsb_apply_zsort_device(tnsb_context* c, int s, int n_arrays, const void* const* d_src, void* const* d_dst, const int* row_bytes)
 {
     int rc = check_set(c, s, "tns::TreeNSearch::apply_zsort");
     if (rc != TNSB_OK) return rc;
     SetState& st = c->sets[s];
     if (!st.zorder_ready) return fail(c, TNSB_ERR_INVALID_STATE, "tns::TreeNSearch::apply_zsort error: no zsort order ready for set_i (" + std::to_string(s) + ").");
-    if (st.n == 0 || stride <= 0) return TNSB_OK;
-    if (!is_device_pointer(d_data)) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb_apply_zsort_device_f32: data must be device memory.");
-    TNSB_CUDA(c, cudaSetDevice(c->device));
-    const size_t bytes = sizeof(float) * (size_t)st.n * stride;
-    TNSB_CUDA(c, c->scan_temp.ensure(bytes, 1.1));
-    TNSB_CUDA(c, cudaMemcpyAsync(c->scan_temp.p, d_data, bytes, cudaMemcpyDeviceToDevice, c->stream));
-    const int64_t total = (int64_t)st.n * stride;
-    gather_rows_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, c->stream>>>(c->scan_temp.as<float>(), d_data, st.d_zorder.as<int32_t>(), st.n, stride);
+    if (n_arrays < 0 || n_arrays > kMaxZsortArrays || (n_arrays > 0 && (!d_src || !d_dst || !row_bytes)))
+        return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb_apply_zsort_device: between 0 and 8 arrays per call.");
+    if (st.n == 0 || n_arrays == 0) return TNSB_OK;
+    DeviceGuard device_guard(c->device);
+    ZsortArrays za;
+    memset(&za, 0, sizeof(za));
+    za.n_arrays = n_arrays;
+    // arrays gathered in place go through one staging buffer (the reference's apply_zsort copies every array too, TreeNSearch.h:452-466)
+    size_t stage_bytes = 0;
+    for (int k = 0; k < n_arrays; k++) {
+        if (row_bytes[k] <= 0 || row_bytes[k] % 4 != 0) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb_apply_zsort_device: row size must be a positive multiple of 4 bytes.");
+        if (!is_device_pointer(d_src[k]) || !is_device_pointer(d_dst[k])) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb_apply_zsort_device: arrays must be device memory.");
+        if (d_src[k] == d_dst[k]) stage_bytes += ((size_t)st.n * row_bytes[k] + 255) & ~(size_t)255;
+    }
+    if (stage_bytes) TNSB_CUDA(c, c->scan_temp.ensure(stage_bytes, 1.1));
+    size_t off = 0;
+    int max_words = 1;
+    for (int k = 0; k < n_arrays; k++) {
+        const size_t bytes = (size_t)st.n * row_bytes[k];
+        za.src[k] = static_cast<const uint32_t*>(d_src[k]);
+        za.dst[k] = static_cast<uint32_t*>(d_dst[k]);
+        za.row_words[k] = row_bytes[k] / 4;
+        max_words = std::max(max_words, za.row_words[k]);
+        if (d_src[k] == d_dst[k]) {
+            uint32_t* stage = reinterpret_cast<uint32_t*>(c->scan_temp.as<char>() + off);
+            TNSB_CUDA(c, cudaMemcpyAsync(stage, d_src[k], bytes, cudaMemcpyDeviceToDevice, c->stream));
+            za.src[k] = stage;
+            off += (bytes + 255) & ~(size_t)255;
+        }
+    }
+    const int64_t total = (int64_t)st.n * max_words;
+    dim3 grid((unsigned)std::min<int64_t>(ceil_div64(total, 256), 64 * c->n_sms), (unsigned)n_arrays);
+    gather_arrays_kernel<<<grid, 256, 0, c->stream>>>(za, st.d_zorder.as<int32_t>(), st.n);
     TNSB_CUDA(c, cudaGetLastError());
     TNSB_CUDA(c, cudaStreamSynchronize(c->stream));
     return TNSB_OK;
+}
+
+int tnsb_apply_zsort_device_f32(tnsb_context* c, int s, float* d_data, int stride)
+{
+    if (stride <= 0) return TNSB_OK;
+    const void* src = d_data;
+    void* dst = d_data;
+    const int row_bytes = 4 * stride;
+    return tnsb_apply_zsort_device(c, s, 1, &src, &dst, &row_bytes);
 }
 
 // ---- multi-GPU (Z-slab) helpers -------------------------------------------------------------------------------------------
 int tnsb_shard_aabb(tnsb_context* c, const float* d_points, int n, int stride, float out_min_max[6])
 {
     if (!c || !out_min_max || (stride != 3 && stride != 4)) return TNSB_ERR_INVALID_ARGUMENT;
-    TNSB_CUDA(c, cudaSetDevice(c->device));
+    DeviceGuard device_guard(c->device);
     TNSB_CUDA(c, c->h_small.ensure(4096));
     TNSB_CUDA(c, c->d_reduce.ensure(64));
     uint32_t* h_red = c->h_small.as<uint32_t>();
@@ -1293,7 +1382,7 @@ int tnsb_shard_aabb(tnsb_context* c, const float* d_points, int n, int stride, f
 int tnsb_shard_histogram(tnsb_context* c, const float* d_points, int n, int stride, int axis, float lo, float hi, int n_bins, uint32_t* d_hist)
 {
     if (!c || !d_hist || axis < 0 || axis > 2 || n_bins < 1 || n_bins > 8192 || (stride != 3 && stride != 4)) return TNSB_ERR_INVALID_ARGUMENT;
-    TNSB_CUDA(c, cudaSetDevice(c->device));
+    DeviceGuard device_guard(c->device);
     TNSB_CUDA(c, cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * (size_t)n_bins, c->stream));
     if (n > 0) {
         const float inv_bin = hi > lo ? (float)n_bins / (hi - lo) : 0.0f;
@@ -1307,7 +1396,7 @@ int tnsb_shard_partition(tnsb_context* c, const float* d_points, int n, int stri
                          float* d_records, int64_t capacity_records, int64_t* counts_out)
 {
     if (!c || !cuts || !counts_out || axis < 0 || axis > 2 || n_parts < 1 || n_parts > kMaxParts || (stride != 3 && stride != 4)) return TNSB_ERR_INVALID_ARGUMENT;
-    TNSB_CUDA(c, cudaSetDevice(c->device));
+    DeviceGuard device_guard(c->device);
     SlabCuts sc;
     sc.n_parts = n_parts;
     sc.halo = halo;
@@ -1339,7 +1428,7 @@ int tnsb_shard_partition(tnsb_context* c, const float* d_points, int n, int stri
 int tnsb_shard_window_create(tnsb_context* c, int64_t cap_owned, int64_t cap_halo, unsigned char* handles_out)
 {
     if (!c || !handles_out || cap_owned < 1 || cap_halo < 1) return TNSB_ERR_INVALID_ARGUMENT;
-    TNSB_CUDA(c, cudaSetDevice(c->device));
+    DeviceGuard device_guard(c->device);
     TNSB_CUDA(c, cudaStreamSynchronize(c->stream));
     for (int p = 0; p < 2; p++) {
         for (int r = 0; r < (int)c->win_peer[p].size(); r++)
@@ -1365,7 +1454,7 @@ int tnsb_shard_window_open(tnsb_context* c, int n_ranks, int my_rank, const unsi
 {
     if (!c || !all_handles || n_ranks < 1 || n_ranks > kMaxParts || my_rank < 0 || my_rank >= n_ranks) return TNSB_ERR_INVALID_ARGUMENT;
     if (!c->win[0].p) return fail(c, TNSB_ERR_INVALID_STATE, "tnsb_shard_window_open: create the window first.");
-    TNSB_CUDA(c, cudaSetDevice(c->device));
+    DeviceGuard device_guard(c->device);
     for (int p = 0; p < 2; p++) {
         c->win_peer[p].assign((size_t)n_ranks, nullptr);
         for (int r = 0; r < n_ranks; r++) {
@@ -1387,7 +1476,7 @@ int tnsb_shard_push(tnsb_context* c, int parity, const float* d_points, int n, i
 {
     if (!c || !cuts || axis < 0 || axis > 2 || (stride != 3 && stride != 4) || parity < 0 || parity > 1) return TNSB_ERR_INVALID_ARGUMENT;
     if (c->win_ranks < 1 || n_parts != c->win_ranks) return fail(c, TNSB_ERR_INVALID_STATE, "tnsb_shard_push: windows are not open for this number of ranks.");
-    TNSB_CUDA(c, cudaSetDevice(c->device));
+    DeviceGuard device_guard(c->device);
     SlabCuts sc;
     sc.n_parts = n_parts;
     sc.halo = halo;
@@ -1409,7 +1498,7 @@ int tnsb_shard_collect(tnsb_context* c, int parity, float** d_records, int64_t* 
 {
     if (!c || !d_records || !n_owned || !n_halo || parity < 0 || parity > 1) return TNSB_ERR_INVALID_ARGUMENT;
     if (c->win_ranks < 1) return fail(c, TNSB_ERR_INVALID_STATE, "tnsb_shard_collect: windows are not open.");
-    TNSB_CUDA(c, cudaSetDevice(c->device));
+    DeviceGuard device_guard(c->device);
     TNSB_CUDA(c, c->h_small.ensure(4096));
     unsigned long long* h = reinterpret_cast<unsigned long long*>(c->h_small.as<char>() + 3072);
     TNSB_CUDA(c, cudaMemcpyAsync(h, c->win[parity].p, 16, cudaMemcpyDeviceToHost, c->stream));
@@ -1466,7 +1555,7 @@ int tnsb_get_pair_neighbor_stats(const tnsb_context* c, int si, int sj, int64_t 
             PairCounters* d = m->d_counters.as<PairCounters>() + id;
             int* h = m->h_small.as<int>();
             h[0] = INT_MAX; h[1] = 0;
-            cudaSetDevice(m->device);
+            DeviceGuard device_guard(m->device);
             cudaMemcpyAsync(d->minmax, h, 2 * sizeof(int), cudaMemcpyHostToDevice, m->stream);
             list_minmax_kernel<<<4 * m->n_sms, 256, 0, m->stream>>>(ps.in_host ? ps.h_ragged.as<int32_t>() : ps.d_ragged.as<int32_t>(), ps.d_list_pos.as<long long>(), ps.n_lists, d->minmax);
             cudaMemcpyAsync(h, d->minmax, 2 * sizeof(int), cudaMemcpyDeviceToHost, m->stream);

@@ -110,8 +110,12 @@ class ShardedSearch:
         self.radius = float(np.float32(radius))
         self.device = torch.device("cuda", device)
         self.engine = TreeNSearch(device)
-        if stream is not None:
-            self.engine.set_stream(stream.cuda_stream)
+        # The exchange step orders the push kernel, the barrier all_reduce and the collect on ONE stream: torch's current stream
+        # unless the caller names another one (the engine's private non-blocking stream would not be ordered behind torch's NCCL calls).
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        self.stream = stream
+        self.engine.set_stream(stream.cuda_stream)
         self.engine.set_search_radius(self.radius)
         self.engine.set_option(L.TNSB_OPT_POINT_STRIDE, 4)
         self._set_added = False
