@@ -250,6 +250,8 @@ class Timer:
         for _ in range(k):
             self.flush.fill_(1)                      # L2 flush, outside the timed pair
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if self.dist is not None:
+                self.dist.barrier()                  # ranks start every timed step together (the flush / sync above de-synchronises them)
             torch.cuda.synchronize()
             e0.record(self.stream)
             step()
@@ -321,7 +323,7 @@ def engine_device_lists(torch, eng, n_lists):
 
     class _Arr:
         def __init__(self, ptr, n, typestr):
-            self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), True), "version": 3, "strides": None}
+            self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 3, "strides": None}
     ragged = torch.as_tensor(_Arr(d_ragged, max(n_ints, 1), "<i4"), device="cuda")
     pos = torch.as_tensor(_Arr(d_pos, max(n_lists, 1), "<i8"), device="cuda")
     return ragged, pos

@@ -208,6 +208,8 @@ int tnsb_shard_window_open(tnsb_context* ctx, int n_ranks, int my_rank, const un
 int tnsb_shard_push(tnsb_context* ctx, int parity, const float* d_points, int n_points, int stride, int id_base, int axis,
                     const float* cuts, int n_parts, float halo, int* d_flag /* device int, raised to 2 when a window overflows; may be NULL */);
 int tnsb_shard_collect(tnsb_context* ctx, int parity, float** d_records, int64_t* n_owned, int64_t* n_halo);
+/* the same, and the value of the barrier's device flag (d_flag after the all_reduce) comes back in the same host round trip */
+int tnsb_shard_collect_flag(tnsb_context* ctx, int parity, float** d_records, int64_t* n_owned, int64_t* n_halo, const int* d_flag, int* flag_out);
 
 /* ---- diagnostics ---------------------------------------------------------------------------------------------------- */
 /* replaces: get_neighborlist_n_bytes()  TreeNSearch.h:246 / .cpp:254-261 */

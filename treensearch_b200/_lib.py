@@ -92,6 +92,7 @@ SIGNATURES = {
     "tnsb_shard_window_open": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "tnsb_shard_push": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_float, _vp]),
     "tnsb_shard_collect": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "tnsb_shard_collect_flag": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(C.c_int64), C.POINTER(C.c_int64), _vp, C.POINTER(C.c_int)]),
     "tnsb_get_neighborlist_n_bytes": (C.c_uint64, [_vp]),
     "tnsb_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "tnsb_get_pair_neighbor_stats": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_int64)]),

@@ -39,8 +39,8 @@ constexpr int kSlabRows = (kBY + 4) * (kBZ + 4);         // 64 candidate rows pe
 constexpr int kQRows = kBY * kBZ;                        // 16 query rows per brick, indexed (z - z0) * 4 + (y - y0)
 constexpr int kTW = kBX + 5;                             // cell boundaries per slab row (odd: spreads the rows over the banks)
 constexpr int kDummy = 256;                              // dummy records (x = 3e38) behind the x plane
-constexpr int kTabH = 30;                                // per-lane range table: 26 ranges + 2 dummy ranges + landing entry + prefetch
-constexpr int kMaxTot = 512;                             // candidates per query on the fast path
+constexpr int kTabH = 32;                                // per-lane range table: 26 ranges + 4 dummy ranges + landing entry + prefetch
+constexpr int kMaxTot = 1024;                            // candidates per query on the fast path (variable radii: cells of r_max / 2 hold many candidates of a small query)
 constexpr int kColStride = 68;                           // bytes between consecutive hits of one lane (34 uint16: conflict-free column reads)
 constexpr uint32_t kBrickSlow = 1u << 24;                // task flag: single cell whose slab does not fit
 
@@ -79,6 +79,7 @@ struct BrickArgs {
     unsigned long long* n_neighbors;
     unsigned long long* n_slow;
     int* max_list;            // longest list written (atomicMax): picks the hit column height of the next run
+    int host_out;             // the ragged buffer is mapped host memory: lists leave the SM as aligned, fully coalesced 128-byte stores
     int* overflow;
 };
 
@@ -312,6 +313,54 @@ __device__ __noinline__ void brick_slow_query(const BrickArgs& a, float qx, floa
     }
 }
 
+
+// slow path of a STAGED brick (the list does not fit the hit column, or the query has more than kMaxTot candidates): one query, the
+// whole warp, candidates from the slab in shared memory (all 25 rows, +-2 cells, no culling), count pass + fill pass
+template <bool SYMMETRIC>
+__device__ __noinline__ void brick_slow_query_staged(const BrickArgs& a, uint32_t slab_a, uint32_t r2_a, const uint16_t* tq, float qx, float qy, float qz, int qid,
+                                                    float r2, int self_off, int lane, unsigned& nb_sum)
+{
+    const unsigned lt = lanemask_lt();
+    int32_t* dst = nullptr;
+    for (int pass = 0; pass < 2; pass++) {
+        int n = 0;
+        for (int row = 0; row < 25; row++) {
+            const uint16_t* trow = tq + ((row / 5) * kRowPitch + (row % 5)) * kTW;
+            const uint32_t lo = trow[0], hi = trow[5];                // byte offsets of cells cx - 2 .. cx + 2 of this row
+            for (uint32_t t0 = lo; t0 < hi; t0 += 32u * 16u) {
+                const uint32_t t = t0 + (uint32_t)lane * 16u;
+                bool hit = false;
+                int id = -1;
+                if (t < hi && (int)t != self_off) {
+                    const float4 v = lds_f4(slab_a + t);
+                    id = __float_as_int(v.w);
+                    const float d2 = dist2(qx, qy, qz, v.x, v.y, v.z);
+                    hit = d2 <= r2;
+                    if (SYMMETRIC) hit = hit || (d2 <= lds_f32(r2_a + (t >> 2)));
+                }
+                const unsigned m = __ballot_sync(kFull, hit);
+                if (pass == 1 && hit) dst[1 + n + __popc(m & lt)] = id;
+                n += __popc(m);
+            }
+        }
+        if (pass == 0) {
+            const unsigned long long need = (unsigned long long)((n + 1 + 3) & ~3);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(a.cursor, need);
+            base = __shfl_sync(kFull, base, 0);
+            if ((long long)(base + need) > a.capacity) {
+                if (lane == 0) *a.overflow = 1;
+                return;
+            }
+            dst = a.ragged + base;
+            if (lane == 0) {
+                dst[0] = n;
+                a.list_pos[qid] = (long long)base;
+            }
+            nb_sum += (unsigned)n;
+        }
+    }
+}
 
 // ---------------------------------------------------------------------------------------------------------------------------
 // warps 0 .. NCONS-1 consume, warp NCONS + b produces into slab buffer b
@@ -640,7 +689,7 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
                 const int off = inc - words;
                 __syncwarp();
                 if (W > 0) {
-                    const unsigned long long need = (unsigned long long)((W + 3) & ~3);
+                    const unsigned long long need = a.host_out ? (unsigned long long)((W + 15) & ~15) : (unsigned long long)((W + 3) & ~3);
                     unsigned long long base = 0;
                     if (lane == 0) base = atomicAdd(a.cursor, need);
                     base = __shfl_sync(kFull, base, 0);
@@ -649,10 +698,30 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
                         // list k = column k of the hit table; (words, offset) of every list are broadcast through the (now idle) range
                         // table instead of shuffles; one coalesced store per 32 list words
                         sts_u32(tab_a, (uint32_t)words | ((uint32_t)off << 8));
+                        sts_u32(tab_a + 128u, (uint32_t)inc);                                  // end offset of list k (flat expansion)
                         __syncwarp();
                         const int32_t* const out_l = a.ragged + base + lane;
                         const uint32_t id_a = slab_a + 12u;
                         const uint32_t tab_w = tab_a - (uint32_t)lane * 4u;
+                        if (a.host_out) {
+                            // mapped host memory: PCIe wants long aligned writes, so the warp walks the FLAT word sequence of its 32 lists
+                            // (word w belongs to the first list whose end offset exceeds w: binary search over the 32 end offsets)
+                            for (int w0 = 0; w0 < W; w0 += 32) {
+                                const int w = w0 + lane;
+                                if (w < W) {
+                                    uint32_t k = (lds_u32(tab_w + 128u + 15u * 4u) <= (uint32_t)w) ? 16u : 0u;
+                                    k += (lds_u32(tab_w + 128u + (k + 7u) * 4u) <= (uint32_t)w) ? 8u : 0u;
+                                    k += (lds_u32(tab_w + 128u + (k + 3u) * 4u) <= (uint32_t)w) ? 4u : 0u;
+                                    k += (lds_u32(tab_w + 128u + (k + 1u) * 4u) <= (uint32_t)w) ? 2u : 0u;
+                                    k += (lds_u32(tab_w + 128u + k * 4u) <= (uint32_t)w) ? 1u : 0u;
+                                    const uint32_t wo = lds_u32(tab_w + k * 4u);
+                                    const int u = w - (int)(wo >> 8);
+                                    int v = (int)(wo & 0xffu) - 1;
+                                    if (u > 0) v = (int)lds_u32(id_a + lds_u16(col_w + (uint32_t)(u - 1) * kColStride + k * 2u));
+                                    stg_cs_at(out_l, (uint32_t)w0, v);
+                                }
+                            }
+                        } else {
                         uint32_t colk = col_w + (uint32_t)lane * kColStride - kColStride;       // entry (lane - 1) of column k
 #pragma unroll 1
                         for (int k0 = 0; k0 < 32; k0 += 4, colk += 8u) {
@@ -682,6 +751,7 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
                                 }
                             }
                         }
+                        }
                     } else if (lane == 0) {
                         *a.overflow = 1;
                     }
@@ -689,12 +759,22 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
                 }
                 // ---- slow path queries, one at a time
                 unsigned sm = __ballot_sync(kFull, slow);
-                while (sm) {
-                    const int src = __ffs(sm) - 1;
-                    sm &= sm - 1;
-                    brick_slow_query<SYMMETRIC>(a, __shfl_sync(kFull, q.x, src), __shfl_sync(kFull, q.y, src), __shfl_sync(kFull, q.z, src), __shfl_sync(kFull, qid, src),
-                                                __shfl_sync(kFull, r2, src), __shfl_sync(kFull, cx, src), __shfl_sync(kFull, cy, src), __shfl_sync(kFull, cz, src), lane, nb_sum);
-                    slow_sum++;
+                if (sm) {
+                    const int ix_s = min(max(cx - x0, 0), ex - 1);
+                    const int tq_s = (rz * kRowPitch + ry) * kTW + ix_s;                       // T entry of cell (cx - 2) of the row (cy - 2, cz - 2)
+                    const int self_s = same_set ? (qp + (int)meta[44 + rr]) * 16 : -1;
+                    while (sm) {
+                        const int src = __ffs(sm) - 1;
+                        sm &= sm - 1;
+                        const float sx = __shfl_sync(kFull, q.x, src), sy = __shfl_sync(kFull, q.y, src), sz = __shfl_sync(kFull, q.z, src), sr = __shfl_sync(kFull, r2, src);
+                        const int sid = __shfl_sync(kFull, qid, src);
+                        if (staged)
+                            brick_slow_query_staged<SYMMETRIC>(a, slab_a, buf_a + SM::kOffR2, sT + __shfl_sync(kFull, tq_s, src), sx, sy, sz, sid, sr,
+                                                               __shfl_sync(kFull, self_s, src), lane, nb_sum);
+                        else
+                            brick_slow_query<SYMMETRIC>(a, sx, sy, sz, sid, sr, __shfl_sync(kFull, cx, src), __shfl_sync(kFull, cy, src), __shfl_sync(kFull, cz, src), lane, nb_sum);
+                        slow_sum++;
+                    }
                 }
                 if (nb_sum > 0x40000000u) {
                     if (lane == 0) atomicAdd(a.n_neighbors, (unsigned long long)nb_sum);

@@ -110,7 +110,9 @@ struct SetState {
     int n_cells = 0;
     bool sorted_valid = false;     // "are_cells_valid" of the reference (TreeNSearch.cpp:148)
     // zsort
-    std::vector<int32_t> zsort_new_to_old;
+    PinBuf h_zorder;               // host copy of the zsort order, fetched lazily by tnsb_get_zsort_order
+    int zorder_n = 0;
+    bool zorder_host_valid = false;
     DevBuf d_zorder;
     bool zorder_ready = false;
 };
@@ -152,7 +154,7 @@ struct tnsb_context {
 
     // options
     bool opt_host_results = true;
-    bool opt_pin_user = false;
+    bool opt_pin_user = true;      // large pageable user arrays are registered (pinned) once: 12 -> 52 GB/s uploads
     int64_t opt_list_capacity = 48;
     int64_t opt_query_limit = -1;
     bool opt_sort_lists = false;
@@ -242,7 +244,8 @@ int stage_input(tnsb_context* c, const void* src, size_t bytes, DevBuf& up, cons
     if (bytes == 0 || !src) { *out = nullptr; return TNSB_OK; }
     if (is_device_pointer(src)) { *out = src; return TNSB_OK; }
     TNSB_CUDA(c, up.ensure(bytes, 1.1));
-    if (c->opt_pin_user && !is_pinned_pointer(src)) {
+    // registration pays from a few MB on (it costs ~0.2 ms per MB once; a pageable copy runs at ~12 GB/s every run)
+    if (c->opt_pin_user && bytes >= ((size_t)4 << 20) && !is_pinned_pointer(src)) {
         auto it = c->registered.find(src);
         if (it == c->registered.end() || it->second < bytes) {
             if (it != c->registered.end()) { cudaHostUnregister(const_cast<void*>(src)); c->registered.erase(it); }
@@ -254,6 +257,16 @@ int stage_input(tnsb_context* c, const void* src, size_t bytes, DevBuf& up, cons
     c->stats.h2d_bytes += (int64_t)bytes;
     *out = up.p;
     return TNSB_OK;
+}
+
+// a borrowed array is being replaced: drop its registration (the caller may free it now)
+void forget_user_array(tnsb_context* c, const void* p)
+{
+    if (!p) return;
+    auto it = c->registered.find(p);
+    if (it == c->registered.end()) return;
+    if (cudaHostUnregister(const_cast<void*>(p)) != cudaSuccess) cudaGetLastError();
+    c->registered.erase(it);
 }
 
 int validate(tnsb_context* c)
@@ -539,8 +552,8 @@ int build_sets_brick(tnsb_context* c, const BrickGrid& bg)
 
 // Variants of the brick query (consumer warps, slab records per buffer, hits per lane column), sized so that one persistent CTA
 // fills the shared memory of an SM: the usual SPH densities (~30 neighbours) / dense clouds (lists up to 128 ids)
-template <bool SYM> struct BrickVariantA { static constexpr int kCons = 16, kSlab = SYM ? 1952 : 2496, kKmax = 64; };
-template <bool SYM> struct BrickVariantB { static constexpr int kCons = 12, kSlab = SYM ? 1488 : 1920, kKmax = 128; };
+template <bool SYM> struct BrickVariantA { static constexpr int kCons = 16, kSlab = SYM ? 1856 : 2384, kKmax = 64; };
+template <bool SYM> struct BrickVariantB { static constexpr int kCons = 12, kSlab = SYM ? 1408 : 1824, kKmax = 128; };
 
 BrickSet brick_set(const SetState& st)
 {
@@ -601,6 +614,7 @@ int query_pair_brick(tnsb_context* c, int si, int sj, PairCounters* d_cnt)
     a.n_neighbors = &d_cnt->n_neighbors;
     a.n_slow = &d_cnt->n_slow;
     a.max_list = &d_cnt->max_list;
+    a.host_out = ps.in_host ? 1 : 0;
     a.overflow = &d_cnt->overflow;
     cudaStream_t s = c->stream;
     brick_plan_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(n_bricks, 8), 8 * c->n_sms), 256, 0, s>>>(bg, a.q.first, a.c.first, slab_cap, a.tasks, a.max_tasks, a.n_tasks, a.plan_overflow);
@@ -1028,7 +1042,7 @@ void tnsb_destroy(tnsb_context* c)
         st.up_pts.release(); st.up_radii.release(); st.cv_pts.release(); st.cv_radii.release();
         for (int b = 0; b < 2; b++) { st.keys[b].release(); st.vals[b].release(); }
         st.sorted.release(); st.sorted_r2.release(); st.cell_key.release(); st.cell_start.release(); st.tile_heads.release();
-        st.htable.release(); st.dense.release(); st.first.release(); st.cursor.release(); st.d_zorder.release();
+        st.htable.release(); st.dense.release(); st.first.release(); st.cursor.release(); st.d_zorder.release(); st.h_zorder.release();
     }
     for (auto& p : c->pairs) { p.d_ragged.release(); p.d_list_pos.release(); p.d_tasks.release(); p.h_ragged.release(); p.h_list_pos.release(); }
     for (int p = 0; p < 2; p++) {
@@ -1087,6 +1101,9 @@ int tnsb_resize_point_set_f32(tnsb_context* c, int s, const float* pts, const fl
     auto& st = c->sets[s];
     // same pointers, same size: nothing changes, the grid of the last run stays valid for prepare_zsort() (TreeNSearch.cpp:77-79, :107-109)
     if (!st.is_f64 && st.u_pts_f32 == pts && st.n == n && (!variable_radius || st.u_radii_f32 == radii)) return TNSB_OK;
+    if (st.u_pts_f32 != pts) forget_user_array(c, st.u_pts_f32);
+    forget_user_array(c, st.u_pts_f64);
+    if (variable_radius && st.u_radii_f32 != radii) forget_user_array(c, st.u_radii_f32);
     st.u_pts_f32 = pts; st.u_pts_f64 = nullptr;
     if (variable_radius) { st.u_radii_f32 = radii; st.u_radii_f64 = nullptr; }
     else if (st.is_f64) { st.u_radii_f32 = nullptr; st.u_radii_f64 = nullptr; }
@@ -1102,6 +1119,9 @@ int tnsb_resize_point_set_f64(tnsb_context* c, int s, const double* pts, const d
     if (rc != TNSB_OK) return rc;
     auto& st = c->sets[s];
     if (st.is_f64 && st.u_pts_f64 == pts && st.n == n && (!variable_radius || st.u_radii_f64 == radii)) return TNSB_OK;     // TreeNSearch.cpp:88-90, :124-126
+    if (st.u_pts_f64 != pts) forget_user_array(c, st.u_pts_f64);
+    forget_user_array(c, st.u_pts_f32);
+    if (variable_radius && st.u_radii_f64 != radii) forget_user_array(c, st.u_radii_f64);
     st.u_pts_f64 = pts; st.u_pts_f32 = nullptr;
     if (variable_radius) { st.u_radii_f64 = radii; st.u_radii_f32 = nullptr; }
     else if (!st.is_f64) { st.u_radii_f32 = nullptr; st.u_radii_f64 = nullptr; }
@@ -1281,11 +1301,11 @@ int tnsb_prepare_zsort(tnsb_context* c)
         if (rc != TNSB_OK) return rc;
     }
     for (auto& st : c->sets) {
-        st.zsort_new_to_old.resize((size_t)st.n);
+        st.zorder_n = st.n;
+        st.zorder_host_valid = false;                 // the host copy is fetched when somebody asks for it (tnsb_get_zsort_order)
         if (st.n == 0) { st.zorder_ready = true; continue; }
         TNSB_CUDA(c, st.d_zorder.ensure(sizeof(int32_t) * (size_t)st.n, 1.1));
         TNSB_CUDA(c, cudaMemcpyAsync(st.d_zorder.p, st.vals[st.sel].p, sizeof(int32_t) * (size_t)st.n, cudaMemcpyDeviceToDevice, c->stream));
-        TNSB_CUDA(c, cudaMemcpyAsync(st.zsort_new_to_old.data(), st.vals[st.sel].p, sizeof(int32_t) * (size_t)st.n, cudaMemcpyDeviceToHost, c->stream));
         st.zorder_ready = true;
         st.sorted_valid = false;      // TreeNSearch.cpp:2660: the user is about to permute the arrays
     }
@@ -1296,12 +1316,20 @@ int tnsb_prepare_zsort(tnsb_context* c)
 int tnsb_get_zsort_order(const tnsb_context* c, int s, const int32_t** new_to_old, int* n_points)
 {
     if (!c || s < 0 || s >= (int)c->sets.size()) return TNSB_ERR_INVALID_ARGUMENT;
-    const SetState& st = c->sets[s];
-    if (!st.zorder_ready || (int)st.zsort_new_to_old.size() != st.n) {
+    SetState& st = const_cast<tnsb_context*>(c)->sets[s];
+    if (!st.zorder_ready || st.zorder_n != st.n) {
         const_cast<tnsb_context*>(c)->err = "tns::TreeNSearch::apply_zsort error: no zsort order ready for set_i (" + std::to_string(s) + ").";
         return TNSB_ERR_INVALID_STATE;
     }
-    if (new_to_old) *new_to_old = st.zsort_new_to_old.data();
+    if (!st.zorder_host_valid && st.n > 0) {
+        tnsb_context* m = const_cast<tnsb_context*>(c);
+        DeviceGuard device_guard(m->device);
+        TNSB_CUDA(m, st.h_zorder.ensure(sizeof(int32_t) * (size_t)st.n, 1.1));
+        TNSB_CUDA(m, cudaMemcpyAsync(st.h_zorder.p, st.d_zorder.p, sizeof(int32_t) * (size_t)st.n, cudaMemcpyDeviceToHost, m->stream));
+        TNSB_CUDA(m, cudaStreamSynchronize(m->stream));
+        st.zorder_host_valid = true;
+    }
+    if (new_to_old) *new_to_old = st.n > 0 ? st.h_zorder.as<int32_t>() : nullptr;
     if (n_points) *n_points = st.n;
     return TNSB_OK;
 }
@@ -1494,7 +1522,14 @@ int tnsb_shard_push(tnsb_context* c, int parity, const float* d_points, int n, i
     return TNSB_OK;
 }
 
+int tnsb_shard_collect_flag(tnsb_context* c, int parity, float** d_records, int64_t* n_owned, int64_t* n_halo, const int* d_flag, int* flag_out);
+
 int tnsb_shard_collect(tnsb_context* c, int parity, float** d_records, int64_t* n_owned, int64_t* n_halo)
+{
+    return tnsb_shard_collect_flag(c, parity, d_records, n_owned, n_halo, nullptr, nullptr);
+}
+
+int tnsb_shard_collect_flag(tnsb_context* c, int parity, float** d_records, int64_t* n_owned, int64_t* n_halo, const int* d_flag, int* flag_out)
 {
     if (!c || !d_records || !n_owned || !n_halo || parity < 0 || parity > 1) return TNSB_ERR_INVALID_ARGUMENT;
     if (c->win_ranks < 1) return fail(c, TNSB_ERR_INVALID_STATE, "tnsb_shard_collect: windows are not open.");
@@ -1502,8 +1537,10 @@ int tnsb_shard_collect(tnsb_context* c, int parity, float** d_records, int64_t* 
     TNSB_CUDA(c, c->h_small.ensure(4096));
     unsigned long long* h = reinterpret_cast<unsigned long long*>(c->h_small.as<char>() + 3072);
     TNSB_CUDA(c, cudaMemcpyAsync(h, c->win[parity].p, 16, cudaMemcpyDeviceToHost, c->stream));
+    if (d_flag && flag_out) TNSB_CUDA(c, cudaMemcpyAsync(h + 2, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));     // the barrier's flag rides on the same round trip
     TNSB_CUDA(c, cudaMemsetAsync(c->win[parity].p, 0, 16, c->stream));     // ready for the step after next (peers wait for the next barrier)
     TNSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (d_flag && flag_out) *flag_out = *reinterpret_cast<int*>(h + 2);
     const int64_t no = (int64_t)h[0], nh = (int64_t)h[1];
     *n_owned = no;
     *n_halo = nh;

@@ -173,9 +173,10 @@ class ShardedSearch:
             self.engine._check(self.engine._lib.tnsb_shard_push(self.engine._h, parity, points.data_ptr(), n, int(points.shape[1]), int(id_base), self.axis,
                                                               cuts_c, self.world, float(halo_width(self.radius)), self._flag.data_ptr()))
             dist.all_reduce(self._flag, op=dist.ReduceOp.MAX)       # barrier (stream ordered behind the push) + re-balance / overflow flag
-            ptr, n_owned, n_halo = C.c_void_p(), C.c_int64(), C.c_int64()
-            rc = self.engine._lib.tnsb_shard_collect(self.engine._h, parity, C.byref(ptr), C.byref(n_owned), C.byref(n_halo))
-            flag = int(self._flag.item())
+            ptr, n_owned, n_halo, flag_c = C.c_void_p(), C.c_int64(), C.c_int64(), C.c_int(0)
+            rc = self.engine._lib.tnsb_shard_collect_flag(self.engine._h, parity, C.byref(ptr), C.byref(n_owned), C.byref(n_halo),
+                                                          self._flag.data_ptr(), C.byref(flag_c))      # counts + flag: ONE host round trip
+            flag = int(flag_c.value)
             if flag < 2:
                 self.engine._check(rc)
                 local = torch.as_tensor(_DeviceRecords(ptr.value, n_owned.value + n_halo.value), device=self.device)
