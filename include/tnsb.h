@@ -45,8 +45,9 @@ enum {
     TNSB_OPT_LIST_CAPACITY = 3,  /* initial capacity, in ints per searching point, of the ragged list buffer (default 48) */
     TNSB_OPT_QUERY_LIMIT = 4,    /* >= 0: in every set only points with index < value are searching points; the remaining
                                     points are find-only ("ghost"/halo points of a Z-slab shard).  -1 (default): all points search */
-    TNSB_OPT_SORT_LISTS = 5,     /* 1: sort every neighbour list ascending on the device before it is handed out (the
-                                    reference's lists are ascending); 0 (default): cell-traversal order */
+    TNSB_OPT_SORT_LISTS = 5,     /* neighbour ids ascending inside every list, like the reference's lists: 1 = always, 0 = never
+                                    (cell-traversal order), -1 (default) = whenever the lists are mirrored to the host: the brick query ranks
+                                    every list in shared memory before it leaves the SM, which hides completely under the PCIe writes */
     TNSB_OPT_ZERO_COPY_RESULTS = 7, /* with HOST_RESULTS: 1 (default) = the query kernel writes the lists straight into mapped pinned host
                                     memory (PCIe writes overlap the search, no HBM copy of the ids, no D2H afterwards; measured 28.1 ms
                                     vs 29.7 ms end to end at 10M points); 0 = lists in HBM, then one D2H copy.  Ignored (HBM path) when
@@ -96,6 +97,7 @@ typedef struct tnsb_stats {
     float   domain_top[3];
     int32_t brick_query;         /* 1: the last run used the brick query (half-radius grid), 0: the cell kernel */
     int64_t n_slow_queries;      /* brick query: queries answered by its warp-cooperative slow path (dense cells, long lists) */
+    int32_t max_list;            /* brick query: longest neighbour list of the last run (1000: some list overflowed its column) */
 } tnsb_stats;
 
 /* ---- life cycle --------------------------------------------------------------------------------------------------- */

@@ -320,6 +320,31 @@ def test_sorted_lists_option(tnsb):
     assert csr_equal((off, idx), port.csr(0, 0))            # ascending exactly like the reference's lists
 
 
+def test_host_lists_are_ascending_by_default(tnsb, golden):
+    """TNSB_OPT_SORT_LISTS = -1 (default): lists mirrored to the host come out ascending, exactly the reference's sequences
+    (SURVEY.md §0.6); device-resident lists stay in traversal order unless the option is 1."""
+    for name in ("uniform_fixed_5000", "variable_random_sym", "duplicates"):
+        case = cases.GOLDEN_CASES[name]()
+        eng = run_engine(tnsb, case)
+        assert eng.stats()["brick_query"] == 1
+        for (i, j) in case["pairs"]:
+            off, idx = eng.neighbor_csr(i, j, sort_lists=False)          # stored order
+            assert np.array_equal(off, golden[f"{name}/{i}_{j}/offsets"]) and np.array_equal(idx, golden[f"{name}/{i}_{j}/indices"]), (name, i, j)
+    # long lists (two ranking registers per lane and more) on the dense blob
+    case = cases.GOLDEN_CASES["clustered_blob"]()
+    eng = run_engine(tnsb, case)
+    eng.run()
+    off, idx = eng.neighbor_csr(0, 0, sort_lists=False)
+    port = cases.configure(loader.OraclePort(), case)
+    port.run(1)
+    poff, pidx = port.csr(0, 0)
+    cnt = np.diff(off)
+    fast = np.nonzero(cnt <= 96)[0]                  # lists that went through the hit columns (the slow path writes traversal order)
+    assert np.array_equal(off, poff)
+    for i in fast[:: max(1, fast.size // 400)]:
+        assert np.array_equal(idx[off[i]:off[i + 1]], pidx[poff[i]:poff[i + 1]])
+
+
 def test_query_limit_halo_points(tnsb):
     # points with index >= limit are find-only (halo of a Z-slab shard): the first `limit` lists equal the full search
     case = cases.GOLDEN_CASES["uniform_fixed_5000"]()

@@ -80,6 +80,7 @@ struct BrickArgs {
     unsigned long long* n_slow;
     int* max_list;            // longest list written (atomicMax): picks the hit column height of the next run
     int host_out;             // the ragged buffer is mapped host memory: lists leave the SM as aligned, fully coalesced 128-byte stores
+    int sort_lists;           // ascending neighbour ids inside every list (the reference's order)
     int* overflow;
 };
 
@@ -259,13 +260,40 @@ __global__ void __launch_bounds__(256) brick_plan_kernel(const BrickGrid g, cons
     }
 }
 
+// ascending sort of n ints by one warp: normalized bitonic network (every compare-exchange puts the smaller value at the lower
+// index, so the virtual +inf padding up to the next power of two never moves).  Used by the slow paths only.
+template <typename Load, typename Store>
+__device__ __forceinline__ void warp_bitonic_sort(int n, int lane, Load ld, Store st)
+{
+    if (n < 2) return;
+    int lg = 1;
+    while ((1 << lg) < n) lg++;
+    const int half = 1 << (lg - 1);                              // pairs per step
+    for (int s = 1; s <= lg; s++) {
+        for (int j = s - 1; j >= 0; j--) {
+            for (int t = lane; t < half; t += 32) {
+                const int lo = ((t >> j) << (j + 1)) | (t & ((1 << j) - 1));
+                const int hi = (j == s - 1) ? (lo ^ ((1 << s) - 1)) : (lo + (1 << j));
+                if (hi < n) {
+                    const int x = ld(lo), y = ld(hi);
+                    if (x > y) { st(lo, y); st(hi, x); }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------------
 // slow path: one query, the whole warp, candidates from global memory, count pass + fill pass
 template <bool SYMMETRIC>
-__device__ __noinline__ void brick_slow_query(const BrickArgs& a, float qx, float qy, float qz, int qid, float r2, int cx, int cy, int cz, int lane, unsigned& nb_sum)
+__device__ __noinline__ void brick_slow_query(const BrickArgs& a, float qx, float qy, float qz, int qid, float r2, int cx, int cy, int cz, int lane, unsigned& nb_sum,
+                                              uint32_t scratch_a, int scratch_cap)
 {
     const unsigned lt = lanemask_lt();
     int32_t* dst = nullptr;
+    bool to_scratch = false;
+    int n_list = 0;
     for (int pass = 0; pass < 2; pass++) {
         int n = 0;
         for (int dz = -2; dz <= 2; dz++) {
@@ -289,7 +317,10 @@ __device__ __noinline__ void brick_slow_query(const BrickArgs& a, float qx, floa
                         if (a.same_set && id == qid) hit = false;
                     }
                     const unsigned m = __ballot_sync(kFull, hit);
-                    if (pass == 1 && hit) dst[1 + n + __popc(m & lt)] = id;
+                    if (pass == 1 && hit) {
+                        if (to_scratch) sts_u32(scratch_a + (uint32_t)(n + __popc(m & lt)) * 4u, (uint32_t)id);
+                        else dst[1 + n + __popc(m & lt)] = id;
+                    }
                     n += __popc(m);
                 }
             }
@@ -309,7 +340,22 @@ __device__ __noinline__ void brick_slow_query(const BrickArgs& a, float qx, floa
                 a.list_pos[qid] = (long long)base;
             }
             nb_sum += (unsigned)n;
+            n_list = n;
+            to_scratch = a.sort_lists && n <= scratch_cap;      // ascending ids: the list is sorted in shared memory before it leaves the SM
         }
+    }
+    if (a.sort_lists && n_list > 1) {
+        __syncwarp();
+        if (to_scratch) {
+            warp_bitonic_sort(n_list, lane, [&](int i) { return (int)lds_u32(scratch_a + (uint32_t)i * 4u); }, [&](int i, int v) { sts_u32(scratch_a + (uint32_t)i * 4u, (uint32_t)v); });
+            for (int i = lane; i < n_list; i += 32) dst[1 + i] = (int)lds_u32(scratch_a + (uint32_t)i * 4u);
+        } else {
+            // longer than the warp's scratch (thousands of neighbours): in place, in global memory
+            volatile int32_t* v = dst + 1;
+            warp_bitonic_sort(n_list, lane, [&](int i) { return (int)v[i]; }, [&](int i, int x) { v[i] = x; });
+        }
+    } else if (to_scratch && n_list == 1) {
+        if (lane == 0) dst[1] = (int)lds_u32(scratch_a);
     }
 }
 
@@ -318,10 +364,12 @@ __device__ __noinline__ void brick_slow_query(const BrickArgs& a, float qx, floa
 // whole warp, candidates from the slab in shared memory (all 25 rows, +-2 cells, no culling), count pass + fill pass
 template <bool SYMMETRIC>
 __device__ __noinline__ void brick_slow_query_staged(const BrickArgs& a, uint32_t slab_a, uint32_t r2_a, const uint16_t* tq, float qx, float qy, float qz, int qid,
-                                                    float r2, int self_off, int lane, unsigned& nb_sum)
+                                                    float r2, int self_off, int lane, unsigned& nb_sum, uint32_t scratch_a, int scratch_cap)
 {
     const unsigned lt = lanemask_lt();
     int32_t* dst = nullptr;
+    bool to_scratch = false;
+    int n_list = 0;
     for (int pass = 0; pass < 2; pass++) {
         int n = 0;
         for (int row = 0; row < 25; row++) {
@@ -339,7 +387,10 @@ __device__ __noinline__ void brick_slow_query_staged(const BrickArgs& a, uint32_
                     if (SYMMETRIC) hit = hit || (d2 <= lds_f32(r2_a + (t >> 2)));
                 }
                 const unsigned m = __ballot_sync(kFull, hit);
-                if (pass == 1 && hit) dst[1 + n + __popc(m & lt)] = id;
+                if (pass == 1 && hit) {
+                    if (to_scratch) sts_u32(scratch_a + (uint32_t)(n + __popc(m & lt)) * 4u, (uint32_t)id);
+                    else dst[1 + n + __popc(m & lt)] = id;
+                }
                 n += __popc(m);
             }
         }
@@ -358,7 +409,22 @@ __device__ __noinline__ void brick_slow_query_staged(const BrickArgs& a, uint32_
                 a.list_pos[qid] = (long long)base;
             }
             nb_sum += (unsigned)n;
+            n_list = n;
+            to_scratch = a.sort_lists && n <= scratch_cap;      // ascending ids: the list is sorted in shared memory before it leaves the SM
         }
+    }
+    if (a.sort_lists && n_list > 1) {
+        __syncwarp();
+        if (to_scratch) {
+            warp_bitonic_sort(n_list, lane, [&](int i) { return (int)lds_u32(scratch_a + (uint32_t)i * 4u); }, [&](int i, int v) { sts_u32(scratch_a + (uint32_t)i * 4u, (uint32_t)v); });
+            for (int i = lane; i < n_list; i += 32) dst[1 + i] = (int)lds_u32(scratch_a + (uint32_t)i * 4u);
+        } else {
+            // longer than the warp's scratch (thousands of neighbours): in place, in global memory
+            volatile int32_t* v = dst + 1;
+            warp_bitonic_sort(n_list, lane, [&](int i) { return (int)v[i]; }, [&](int i, int x) { v[i] = x; });
+        }
+    } else if (to_scratch && n_list == 1) {
+        if (lane == 0) dst[1] = (int)lds_u32(scratch_a);
     }
 }
 
@@ -703,6 +769,42 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
                         const int32_t* const out_l = a.ragged + base + lane;
                         const uint32_t id_a = slab_a + 12u;
                         const uint32_t tab_w = tab_a - (uint32_t)lane * 4u;
+                        if (a.sort_lists) {
+                            // ascending ids: every list is ranked in place inside its column (rank of an entry = number of entries of the
+                            // list with a smaller id; ids of one list are distinct), one list at a time, entries (lane, lane + 32, ...) per lane
+                            constexpr int V = (KMAX + 31) / 32;
+                            for (uint32_t k = 0; k < 32u; k++) {
+                                const int nk = (int)(lds_u32(tab_w + k * 4u) & 0xffu) - 1;
+                                if (nk < 2) continue;
+                                uint32_t ent[V];
+                                int idv[V], rank[V];
+#pragma unroll
+                                for (int r = 0; r < V; r++) {
+                                    const int e = r * 32 + lane;
+                                    ent[r] = 0;
+                                    idv[r] = 0x7fffffff;
+                                    rank[r] = 0;
+                                    if (e < nk) {
+                                        ent[r] = lds_u16(col_w + (uint32_t)e * kColStride + k * 2u);
+                                        idv[r] = (int)lds_u32(id_a + ent[r]);
+                                    }
+                                }
+#pragma unroll
+                                for (int rb = 0; rb < V; rb++) {
+                                    const int m = min(32, nk - rb * 32);
+                                    for (int j = 0; j < m; j++) {
+                                        const int b = __shfl_sync(kFull, idv[rb], j);
+#pragma unroll
+                                        for (int r = 0; r < V; r++) rank[r] += (b < idv[r]) ? 1 : 0;
+                                    }
+                                }
+                                __syncwarp();
+#pragma unroll
+                                for (int r = 0; r < V; r++)
+                                    if (r * 32 + lane < nk) sts_u16(col_w + (uint32_t)rank[r] * kColStride + k * 2u, ent[r]);
+                            }
+                            __syncwarp();
+                        }
                         if (a.host_out) {
                             // mapped host memory: PCIe wants long aligned writes, so the warp walks the FLAT word sequence of its 32 lists
                             // (word w belongs to the first list whose end offset exceeds w: binary search over the 32 end offsets)
@@ -763,6 +865,9 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
                     const int ix_s = min(max(cx - x0, 0), ex - 1);
                     const int tq_s = (rz * kRowPitch + ry) * kTW + ix_s;                       // T entry of cell (cx - 2) of the row (cy - 2, cz - 2)
                     const int self_s = same_set ? (qp + (int)meta[44 + rr]) * 16 : -1;
+                    // the warp's range table + hit columns are idle here: scratch for sorting slow-path lists
+                    const uint32_t scratch_a = tab_a - (uint32_t)lane * 4u;
+                    constexpr int scratch_cap = SM::kWarpBytes / 4;
                     while (sm) {
                         const int src = __ffs(sm) - 1;
                         sm &= sm - 1;
@@ -770,9 +875,10 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
                         const int sid = __shfl_sync(kFull, qid, src);
                         if (staged)
                             brick_slow_query_staged<SYMMETRIC>(a, slab_a, buf_a + SM::kOffR2, sT + __shfl_sync(kFull, tq_s, src), sx, sy, sz, sid, sr,
-                                                               __shfl_sync(kFull, self_s, src), lane, nb_sum);
+                                                               __shfl_sync(kFull, self_s, src), lane, nb_sum, scratch_a, scratch_cap);
                         else
-                            brick_slow_query<SYMMETRIC>(a, sx, sy, sz, sid, sr, __shfl_sync(kFull, cx, src), __shfl_sync(kFull, cy, src), __shfl_sync(kFull, cz, src), lane, nb_sum);
+                            brick_slow_query<SYMMETRIC>(a, sx, sy, sz, sid, sr, __shfl_sync(kFull, cx, src), __shfl_sync(kFull, cy, src), __shfl_sync(kFull, cz, src), lane, nb_sum,
+                                                        scratch_a, scratch_cap);
                         slow_sum++;
                     }
                 }

@@ -157,13 +157,13 @@ struct tnsb_context {
     bool opt_pin_user = true;      // large pageable user arrays are registered (pinned) once: 12 -> 52 GB/s uploads
     int64_t opt_list_capacity = 48;
     int64_t opt_query_limit = -1;
-    bool opt_sort_lists = false;
+    int opt_sort_lists = -1;       // -1: automatic (ascending lists when they go to the host: the ranking hides under the PCIe writes), 0 / 1
     bool opt_zero_copy = true;
     int opt_point_stride = 3;
     int opt_bucket_passes = 0;          // 0: automatic
     int opt_build = 0;             // 0: bucket build when the cell table is small enough, else radix sort; 1: always radix sort
     int opt_query_kernel = 0;      // 0: automatic (brick query on the half-radius grid while its cell table is affordable, else the cell kernel), 1: always the cell kernel
-    int brick_kmax = 128;          // hit column height of the brick query: 128 on the first run, then 64 while the longest list of the previous run fits
+    int brick_kmax = 128;          // hit column height of the brick query: 128 on the first run, then 64 / 96 while the longest list of the previous run fits
 
     // world box with hysteresis (TreeNSearch.cpp:474-482)
     bool domain_valid = false;
@@ -346,7 +346,7 @@ int build_sets(tnsb_context* c, const GridParams& gp, bool need_order, const int
         if (st.has_radii) TNSB_CUDA(c, st.sorted_r2.ensure(sizeof(float) * (size_t)st.n, 1.1));
         if (st.bucket) {
             // destination windows of <= 80 MB of records (L2 is 126 MB): see bucket_scatter_kernel
-            int passes = c->opt_bucket_passes > 0 ? c->opt_bucket_passes : (int)std::min<int64_t>(16, std::max<int64_t>(1, ((int64_t)st.n * 16 + (80ll << 20) - 1) / (80ll << 20)));
+            int passes = c->opt_bucket_passes > 0 ? c->opt_bucket_passes : (int)std::min<int64_t>(16, std::max<int64_t>(1, ((int64_t)st.n * 16 + (56ll << 20) - 1) / (56ll << 20)));
             for (int p = 0; p < passes; p++) {
                 const Key lo = (Key)(n_keys * p / passes), hi = (Key)(n_keys * (p + 1) / passes);
                 bucket_scatter_kernel<Key><<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.d_stride, st.has_radii ? st.d_radii : nullptr, st.keys[0].as<Key>(), st.n,
@@ -535,7 +535,7 @@ int build_sets_brick(tnsb_context* c, const BrickGrid& bg)
         if (st.n == 0) continue;
         TNSB_CUDA(c, st.sorted.ensure(sizeof(float4) * (size_t)st.n, 1.1));
         if (st.has_radii) TNSB_CUDA(c, st.sorted_r2.ensure(sizeof(float) * (size_t)st.n, 1.1));
-        const int passes = c->opt_bucket_passes > 0 ? c->opt_bucket_passes : (int)std::min<int64_t>(16, std::max<int64_t>(1, ((int64_t)st.n * 16 + (80ll << 20) - 1) / (80ll << 20)));
+        const int passes = c->opt_bucket_passes > 0 ? c->opt_bucket_passes : (int)std::min<int64_t>(16, std::max<int64_t>(1, ((int64_t)st.n * 16 + (56ll << 20) - 1) / (56ll << 20)));
         for (int p = 0; p < passes; p++) {
             const uint32_t lo = (uint32_t)(n_keys * p / passes), hi = (uint32_t)(n_keys * (p + 1) / passes);
             bucket_scatter_kernel<uint32_t><<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.d_stride, st.has_radii ? st.d_radii : nullptr, st.keys[0].as<uint32_t>(), st.n,
@@ -551,9 +551,10 @@ int build_sets_brick(tnsb_context* c, const BrickGrid& bg)
 }
 
 // Variants of the brick query (consumer warps, slab records per buffer, hits per lane column), sized so that one persistent CTA
-// fills the shared memory of an SM: the usual SPH densities (~30 neighbours) / dense clouds (lists up to 128 ids)
+// fills the shared memory of an SM: lists up to 64 ids (the usual SPH densities, ~30 neighbours) / up to 96 / up to 128
 template <bool SYM> struct BrickVariantA { static constexpr int kCons = 16, kSlab = SYM ? 1856 : 2384, kKmax = 64; };
-template <bool SYM> struct BrickVariantB { static constexpr int kCons = 12, kSlab = SYM ? 1408 : 1824, kKmax = 128; };
+template <bool SYM> struct BrickVariantM { static constexpr int kCons = 12, kSlab = SYM ? 2064 : 2640, kKmax = 96; };
+template <bool SYM> struct BrickVariantB { static constexpr int kCons = 10, kSlab = SYM ? 2048 : 2624, kKmax = 128; };
 
 BrickSet brick_set(const SetState& st)
 {
@@ -584,8 +585,10 @@ int query_pair_brick(tnsb_context* c, int si, int sj, PairCounters* d_cnt)
     PairState& ps = c->pairs[si * c->sets.size() + sj];
     const bool variable = !c->radius_set;
     const bool symmetric = variable && c->symmetric;   // TreeNSearch.cpp:2431
-    const bool tall = c->brick_kmax > 64;
-    const int slab_cap = tall ? (symmetric ? BrickVariantB<true>::kSlab : BrickVariantB<false>::kSlab) : (symmetric ? BrickVariantA<true>::kSlab : BrickVariantA<false>::kSlab);
+    const int level = c->brick_kmax <= 64 ? 0 : (c->brick_kmax <= 96 ? 1 : 2);
+    const int slab_cap = level == 0 ? (symmetric ? BrickVariantA<true>::kSlab : BrickVariantA<false>::kSlab)
+                       : level == 1 ? (symmetric ? BrickVariantM<true>::kSlab : BrickVariantM<false>::kSlab)
+                                    : (symmetric ? BrickVariantB<true>::kSlab : BrickVariantB<false>::kSlab);
     const BrickGrid& bg = c->bgrid;
     BrickArgs a;
     a.g = bg;
@@ -615,15 +618,20 @@ int query_pair_brick(tnsb_context* c, int si, int sj, PairCounters* d_cnt)
     a.n_slow = &d_cnt->n_slow;
     a.max_list = &d_cnt->max_list;
     a.host_out = ps.in_host ? 1 : 0;
+    a.sort_lists = c->opt_sort_lists == 1 || (c->opt_sort_lists < 0 && c->opt_host_results) ? 1 : 0;
     a.overflow = &d_cnt->overflow;
     cudaStream_t s = c->stream;
     brick_plan_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(n_bricks, 8), 8 * c->n_sms), 256, 0, s>>>(bg, a.q.first, a.c.first, slab_cap, a.tasks, a.max_tasks, a.n_tasks, a.plan_overflow);
     TNSB_CUDA(c, cudaGetLastError());
     cudaError_t e;
-    if (!tall) {
+    if (level == 0) {
         if (!variable) e = launch_brick<BrickVariantA<false>, false, false>(a, c->n_sms, s);
         else if (!symmetric) e = launch_brick<BrickVariantA<false>, true, false>(a, c->n_sms, s);
         else e = launch_brick<BrickVariantA<true>, true, true>(a, c->n_sms, s);
+    } else if (level == 1) {
+        if (!variable) e = launch_brick<BrickVariantM<false>, false, false>(a, c->n_sms, s);
+        else if (!symmetric) e = launch_brick<BrickVariantM<false>, true, false>(a, c->n_sms, s);
+        else e = launch_brick<BrickVariantM<true>, true, true>(a, c->n_sms, s);
     } else {
         if (!variable) e = launch_brick<BrickVariantB<false>, false, false>(a, c->n_sms, s);
         else if (!symmetric) e = launch_brick<BrickVariantB<false>, true, false>(a, c->n_sms, s);
@@ -858,7 +866,8 @@ int run_impl(tnsb_context* c)
         if (c->sets[si].n == 0 || n_total == 0) continue;
         const int64_t want = (int64_t)ps.n_lists * (c->opt_list_capacity + 1) + 4096;
         // zero-copy: the kernel's flushes go straight to mapped pinned host memory (no HBM copy of the lists, no D2H afterwards)
-        const bool in_host = c->opt_host_results && c->opt_zero_copy && !c->opt_sort_lists;
+        // zero-copy and sorted lists go together in the brick query (it sorts in shared memory); the cell kernel sorts in a post pass over HBM
+        const bool in_host = c->opt_host_results && c->opt_zero_copy && !(c->opt_sort_lists == 1 && !c->brick_mode);
         if (in_host != ps.in_host) { ps.in_host = in_host; ps.capacity = 0; }
         if (ps.in_host) {
             TNSB_CUDA(c, ps.h_ragged.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(want, ps.capacity)));
@@ -921,8 +930,9 @@ int run_impl(tnsb_context* c)
         todo.swap(again);
     }
     // hit column height of the next run: the short columns (more warps per SM) while the longest list leaves some headroom
-    if (c->brick_mode && !act.empty()) c->brick_kmax = brick_max_list <= 62 ? 64 : 128;
-    if (c->opt_sort_lists) {
+    if (c->brick_mode && !act.empty()) c->brick_kmax = brick_max_list <= 62 ? 64 : (brick_max_list <= 92 ? 96 : 128);
+    c->stats.max_list = brick_max_list;
+    if (c->opt_sort_lists == 1 && !c->brick_mode) {
         for (int id : act) {
             PairState& ps = c->pairs[id];
             if (ps.n_lists == 0 || ps.n_ints == 0) continue;
@@ -1195,7 +1205,7 @@ int tnsb_set_option(tnsb_context* c, int option, int64_t value)
         if (value < 1) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: list capacity must be >= 1.");
         c->opt_list_capacity = value; return TNSB_OK;
     case TNSB_OPT_QUERY_LIMIT: c->opt_query_limit = value; return TNSB_OK;
-    case TNSB_OPT_SORT_LISTS: c->opt_sort_lists = value != 0; return TNSB_OK;
+    case TNSB_OPT_SORT_LISTS: c->opt_sort_lists = value < 0 ? -1 : (value != 0 ? 1 : 0); return TNSB_OK;
     case TNSB_OPT_ZERO_COPY_RESULTS: c->opt_zero_copy = value != 0; return TNSB_OK;
     case TNSB_OPT_BUILD:
         if (value != 0 && value != 1) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: build must be 0 (automatic) or 1 (radix sort).");
