@@ -98,6 +98,7 @@ typedef struct tnsb_stats {
     int32_t brick_query;         /* 1: the last run used the brick query (half-radius grid), 0: the cell kernel */
     int64_t n_slow_queries;      /* brick query: queries answered by its warp-cooperative slow path (dense cells, long lists) */
     int32_t max_list;            /* brick query: longest neighbour list of the last run (1000: some list overflowed its column) */
+    int32_t speculative_grid;    /* 1: the last run reused the previous run's grid without waiting for the world box (checked on the device) */
 } tnsb_stats;
 
 /* ---- life cycle --------------------------------------------------------------------------------------------------- */

@@ -577,6 +577,47 @@ def test_cell_size_semantics(tnsb):
         eng.run()
 
 
+def test_speculative_grid_reuse_and_fallback(tnsb):
+    """Steady state: run() reuses the previous grid without waiting for the world box (one host round trip per run); a device-side
+    check notices when the cloud leaves that grid -- or the radii change -- and the run repeats itself with a fresh grid."""
+    rs = np.random.RandomState(3)
+    pts = (rs.random_sample((30_000, 3)) * 2.0).astype(np.float32)
+    r = 0.08
+    eng = tnsb.TreeNSearch()
+    eng.set_search_radius(r)
+    eng.add_point_set(pts)
+    eng.set_active_search(0, 0, True)
+    eng.run()
+    assert eng.stats()["speculative_grid"] == 0
+    pts += np.float32(0.01)                                     # small motion: still inside the grid (4 cells of room)
+    eng.run()
+    st = eng.stats()
+    assert st["speculative_grid"] == 1 and st["n_reruns"] == 0
+    assert_matches_port(eng, dict(sets=[(pts, None)], radius=r, pairs=[(0, 0)], symmetric=True))
+    pts[:1000] += np.float32(0.7)                               # a splash outside the old grid
+    eng.run()
+    st = eng.stats()
+    assert st["n_reruns"] >= 1 and st["speculative_grid"] == 0
+    assert_matches_port(eng, dict(sets=[(pts, None)], radius=r, pairs=[(0, 0)], symmetric=True))
+    eng.run()
+    assert eng.stats()["speculative_grid"] == 1
+    eng.set_search_radius(0.05)                                 # a different radius never reuses the old grid
+    eng.run()
+    assert eng.stats()["speculative_grid"] == 0
+    assert_matches_port(eng, dict(sets=[(pts, None)], radius=0.05, pairs=[(0, 0)], symmetric=True))
+    # variable radii: the device check also watches the radius range
+    rad = np.full(pts.shape[0], 0.06, np.float32)
+    e2 = tnsb.TreeNSearch()
+    e2.add_point_set(pts, rad)
+    e2.set_active_search(0, 0, True)
+    e2.run(); e2.run()
+    assert e2.stats()["speculative_grid"] == 1
+    rad[::7] = 0.09                                             # larger than the grid was built for
+    e2.run()
+    assert e2.stats()["n_reruns"] >= 1
+    assert_matches_port(e2, dict(sets=[(pts, rad)], radius=None, pairs=[(0, 0)], symmetric=True))
+
+
 def test_resize_fast_path_keeps_grid(tnsb):
     """resize_point_set with the same pointer and size is a no-op (TreeNSearch.cpp:77-79, :107-109): the grid stays valid for prepare_zsort."""
     import torch

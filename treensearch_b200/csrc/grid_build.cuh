@@ -270,6 +270,28 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(const float* __rest
     }
 }
 
+// Speculative reuse of the previous run's brick grid (no host round trip for the world box): one thread checks the fresh
+// box / radius range in `red` (ordered-uint encoding, see aabb_kernel) against the grid the build is about to use and raises *flag
+// when a point would fall outside it, or when the largest radius no longer matches the cell size.  The host reads the flag together
+// with the query counters at the end of the run and repeats the run with a fresh grid if it is set.
+__global__ void box_check_kernel(const uint32_t* __restrict__ red, BrickGrid g, float r_max_grid, int variable_radius, int* __restrict__ flag)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    bool bad = false;
+    const int dims[3] = { g.nx, g.ny, g.nz };
+    for (int d = 0; d < 3; d++) {
+        const float lo = ordered_to_float(red[d]), hi = ordered_to_float(red[3 + d]);
+        if (!(lo == lo) || !(hi == hi) || isinf(lo) || isinf(hi)) bad = true;
+        const double clo = floor(((double)lo - g.bottom[d]) * g.inv_cell), chi = floor(((double)hi - g.bottom[d]) * g.inv_cell);
+        if (clo < 0.0 || chi > (double)(dims[d] - 1)) bad = true;
+    }
+    if (variable_radius) {
+        const float r_lo = ordered_to_float(red[6]), r_hi = ordered_to_float(red[7]);
+        if (!(r_lo > 0.0f) || !(r_hi <= r_max_grid) || r_hi < 0.8f * r_max_grid) bad = true;
+    }
+    if (bad) *flag = 1;
+}
+
 // occupied cells of the prefix table first[0 .. n_keys]: count per tile, then (after a scan of the tile counts) emit
 // cell_key / cell_start in key order; optionally fills the cell kernel's dense {start, end} table for every key
 __global__ void __launch_bounds__(kCellThreads) table_count_kernel(const uint32_t* __restrict__ first, int64_t n_keys, uint32_t* __restrict__ tile_cells)

@@ -172,6 +172,11 @@ struct tnsb_context {
     double r_max = 0.0;            // largest search distance of the last build
     int bits = 0;
     bool key64 = false;
+    // speculative reuse of the last brick grid: valid while the configuration it was built for is unchanged
+    bool spec_valid = false, spec_used = false;
+    int spec_n_sets = 0;
+    float spec_radius = 0.0f;
+    int opt_speculate = 1;
     bool brick_mode = false;       // grid built last: half-radius cells + linear row keys (brick query) or cell = r + 3-D Morton keys (cell kernel, zsort)
     BrickGrid bgrid;
 
@@ -685,6 +690,7 @@ int build_grid(tnsb_context* c, GridParams* gp_out, bool want_brick, bool need_o
     TNSB_CUDA(c, c->h_small.ensure(4096));
     TNSB_CUDA(c, c->d_reduce.ensure(64));
     TNSB_CUDA(c, cudaEventRecord(c->ev[EV_BEGIN], s));
+    c->spec_used = false;
 
     // ---- upload (or adopt device pointers)
     const void* raw_pts[64];
@@ -708,7 +714,8 @@ int build_grid(tnsb_context* c, GridParams* gp_out, bool want_brick, bool need_o
     // ---- world box + radius range (and double -> float conversion)
     uint32_t* h_red = c->h_small.as<uint32_t>();
     for (int k = 0; k < 8; k++) h_red[k] = ((k < 3) || (k == 6)) ? 0xffffffffu : 0u;
-    TNSB_CUDA(c, cudaMemcpyAsync(c->d_reduce.p, h_red, 32, cudaMemcpyHostToDevice, s));
+    h_red[8] = 0u;                                      // word 8: "the speculative grid does not fit" flag (box_check_kernel)
+    TNSB_CUDA(c, cudaMemcpyAsync(c->d_reduce.p, h_red, 36, cudaMemcpyHostToDevice, s));
     const int aabb_grid = 4 * c->n_sms;
     for (int si = 0; si < n_sets; si++) {
         auto& st = c->sets[si];
@@ -730,9 +737,26 @@ int build_grid(tnsb_context* c, GridParams* gp_out, bool want_brick, bool need_o
         }
         c->stats.n_kernel_launches++;
     }
-    TNSB_CUDA(c, cudaMemcpyAsync(h_red + 8, c->d_reduce.p, 32, cudaMemcpyDeviceToHost, s));
+    // ---- steady state: the grid of the previous run is reused WITHOUT waiting for the box (a device-side check decides at the end of
+    // the run whether that was legitimate): one host round trip per run() instead of two
+    if (want_brick && !need_order && c->opt_speculate && c->spec_valid && c->spec_n_sets == n_sets &&
+        (c->radius_set ? c->spec_radius == c->radius : c->spec_radius < 0.0f)) {
+        box_check_kernel<<<1, 32, 0, s>>>(c->d_reduce.as<uint32_t>(), c->bgrid, (float)c->r_max, c->radius_set ? 0 : 1, c->d_reduce.as<int>() + 8);
+        TNSB_CUDA(c, cudaEventRecord(c->ev[EV_AABB], s));
+        c->stats.n_kernel_launches++;
+        c->spec_used = true;
+        c->stats.speculative_grid = 1;
+        c->brick_mode = true;
+        c->stats.cell_size = (float)(0.5 * c->cell);
+        c->stats.key_bits = 3 * c->bits;
+        c->stats.brick_query = 1;
+        for (int d = 0; d < 3; d++) { c->stats.domain_bottom[d] = (float)c->dom_bottom[d]; c->stats.domain_top[d] = (float)c->dom_top[d]; }
+        return build_sets_brick(c, c->bgrid);
+    }
+    TNSB_CUDA(c, cudaMemcpyAsync(h_red + 16, c->d_reduce.p, 32, cudaMemcpyDeviceToHost, s));
     TNSB_CUDA(c, cudaEventRecord(c->ev[EV_AABB], s));
     TNSB_CUDA(c, cudaStreamSynchronize(s));
+    h_red += 8;                                          // the results sit at h_red[8 .. 15] below
     float lo[3], hi[3];
     for (int d = 0; d < 3; d++) { lo[d] = ordered_to_float(h_red[8 + d]); hi[d] = ordered_to_float(h_red[8 + 3 + d]); }
     double r_max = c->radius_set ? (double)c->radius : (double)ordered_to_float(h_red[8 + 7]);
@@ -789,13 +813,14 @@ int build_grid(tnsb_context* c, GridParams* gp_out, bool want_brick, bool need_o
     // ---- brick query grid: half-radius cells over the occupied extent, linear row keys.  Taken while its prefix table (one
     // uint32 per cell and per set) is small next to the point count; huge sparse domains keep the cell kernel + hash.
     c->brick_mode = false;
+    c->spec_valid = false;
     if (want_brick && !need_order) {
         BrickGrid bg;
         int64_t dims[3];
         bg.inv_cell = 2.0 / c->cell;
         for (int d = 0; d < 3; d++) {
             bg.bottom[d] = c->dom_bottom[d];
-            dims[d] = (int64_t)std::floor(((double)hi[d] - bg.bottom[d]) * bg.inv_cell) + 1;
+            dims[d] = (int64_t)std::floor(((double)hi[d] - bg.bottom[d]) * bg.inv_cell) + 1 + 4;      // + 4 cells (2 r): room for the cloud to move while the grid is reused
         }
         int64_t n_max = 0;
         for (auto& st : c->sets) n_max = std::max<int64_t>(n_max, st.n);
@@ -804,6 +829,9 @@ int build_grid(tnsb_context* c, GridParams* gp_out, bool want_brick, bool need_o
             bg.nx = (int)dims[0]; bg.ny = (int)dims[1]; bg.nz = (int)dims[2];
             c->bgrid = bg;
             c->brick_mode = true;
+            c->spec_valid = true;
+            c->spec_n_sets = n_sets;
+            c->spec_radius = c->radius_set ? c->radius : -1.0f;
             c->stats.cell_size = (float)(0.5 * c->cell);
             c->stats.brick_query = 1;
             return build_sets_brick(c, bg);
@@ -818,6 +846,8 @@ float ev_ms(tnsb_context* c, int a, int b)
     if (cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]) != cudaSuccess) { cudaGetLastError(); return 0.0f; }
     return ms;
 }
+
+int run_impl(tnsb_context* c);
 
 int run_impl(tnsb_context* c)
 {
@@ -897,7 +927,19 @@ int run_impl(tnsb_context* c)
             if (rc != TNSB_OK) return rc;
         }
         TNSB_CUDA(c, cudaMemcpyAsync(h_out, c->d_counters.p, sizeof(PairCounters) * n_pairs, cudaMemcpyDeviceToHost, s));
+        int* const h_spec_flag = c->h_small.as<int>() + 32;
+        *h_spec_flag = 0;
+        if (c->spec_used) TNSB_CUDA(c, cudaMemcpyAsync(h_spec_flag, c->d_reduce.as<int>() + 8, sizeof(int), cudaMemcpyDeviceToHost, s));
         TNSB_CUDA(c, cudaStreamSynchronize(s));
+        if (c->spec_used && *h_spec_flag) {
+            // the cloud left the grid that was reused speculatively (or the radius range changed): this run's lists are void.
+            // Repeat the whole run with a grid fitted to the fresh box (one extra host round trip, rare).
+            c->spec_valid = false;
+            const int reruns = c->stats.n_reruns + 1;
+            const int rc2 = run_impl(c);
+            c->stats.n_reruns += reruns;
+            return rc2;
+        }
         std::vector<int> again;
         for (int id : todo) {
             PairState& ps = c->pairs[id];
@@ -1037,6 +1079,7 @@ int tnsb_create(tnsb_context** out, int device)
     if (const char* qk = getenv("TNSB_QUERY_KERNEL")) c->opt_query_kernel = (qk[0] == '0') ? 0 : 1;      // A/B switches for tests and profiling
     if (const char* bk = getenv("TNSB_BUILD")) c->opt_build = (bk[0] == '1') ? 1 : 0;
     if (const char* bp = getenv("TNSB_BUCKET_PASSES")) c->opt_bucket_passes = atoi(bp);
+    if (const char* sp = getenv("TNSB_SPECULATE")) c->opt_speculate = atoi(sp) != 0;
     for (int k = 0; k < EV_COUNT; k++) cudaEventCreate(&c->ev[k]);
     *out = c;
     return TNSB_OK;
