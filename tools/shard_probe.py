@@ -17,6 +17,16 @@ S = job.search
 S.engine.set_option(L.TNSB_OPT_HOST_RESULTS, 0)
 for _ in range(3):
     job.step_device()
+import re, subprocess
+def nvlink_kib(gpu):
+    """Sum of the NVLink data counters (KiB transmitted, KiB received) of one GPU (nvidia-smi nvlink -gt d)."""
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(gpu)], capture_output=True, text=True, timeout=20).stdout
+    except Exception:
+        return None
+    tx = sum(int(x) for x in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out))
+    rx = sum(int(x) for x in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out))
+    return tx, rx
 acc = {}
 def tick(name, t0):
     torch.cuda.synchronize()
@@ -48,7 +58,18 @@ for _ in range(K):
     eng.set_option(L.TNSB_OPT_QUERY_LIMIT, S.n_owned)
     eng.resize_point_set(0, S.local, n_points=S.local.shape[0]); t = tick("resize", t)
     eng.run(); t = tick("run", t)
+# NVLink bytes of K un-instrumented steps (counters of this rank's GPU) next to the algorithmic bytes of the exchange
+dist.barrier(); torch.cuda.synchronize()
+nv0 = nvlink_kib(lr)
+for _ in range(K):
+    job.step_device()
+dist.barrier(); torch.cuda.synchronize()
+nv1 = nvlink_kib(lr)
 if rank == 0:
+    if nv0 and nv1:
+        tx, rx = (nv1[0] - nv0[0]) * 1024.0 / K, (nv1[1] - nv0[1]) * 1024.0 / K
+        print(f"nvlink per step (rank 0 GPU): tx {tx / 1e6:.2f} MB, rx {rx / 1e6:.2f} MB; algorithmic: halo records received {S.n_halo * 16 / 1e6:.2f} MB "
+              f"(+ migrating owned records), {S.n_halo} halo points of {S.n_owned} owned = {100.0 * S.n_halo / max(S.n_owned, 1):.2f} %")
     st = eng.stats()
     print(S.exchange, {k: round(v / K, 3) for k, v in acc.items()}, "n_owned", S.n_owned, "n_halo", S.n_halo,
           {k: round(st[k], 3) for k in ("ms_aabb", "ms_keys", "ms_sort", "ms_reorder", "ms_query", "ms_total_device", "ms_wall")}, "slow", st["n_slow_queries"])
