@@ -177,6 +177,7 @@ struct tnsb_context {
     int spec_n_sets = 0;
     float spec_radius = 0.0f;
     int opt_speculate = 1;
+    int opt_force_level = -1;
     bool brick_mode = false;       // grid built last: half-radius cells + linear row keys (brick query) or cell = r + 3-D Morton keys (cell kernel, zsort)
     BrickGrid bgrid;
 
@@ -590,7 +591,8 @@ int query_pair_brick(tnsb_context* c, int si, int sj, PairCounters* d_cnt)
     PairState& ps = c->pairs[si * c->sets.size() + sj];
     const bool variable = !c->radius_set;
     const bool symmetric = variable && c->symmetric;   // TreeNSearch.cpp:2431
-    const int level = c->brick_kmax <= 64 ? 0 : (c->brick_kmax <= 96 ? 1 : 2);
+    int level = c->brick_kmax <= 64 ? 0 : (c->brick_kmax <= 96 ? 1 : 2);
+    if (c->opt_force_level >= 0) level = c->opt_force_level;      // TNSB_BRICK_LEVEL=0|1|2: experiments only
     const int slab_cap = level == 0 ? (symmetric ? BrickVariantA<true>::kSlab : BrickVariantA<false>::kSlab)
                        : level == 1 ? (symmetric ? BrickVariantM<true>::kSlab : BrickVariantM<false>::kSlab)
                                     : (symmetric ? BrickVariantB<true>::kSlab : BrickVariantB<false>::kSlab);
@@ -1080,6 +1082,7 @@ int tnsb_create(tnsb_context** out, int device)
     if (const char* bk = getenv("TNSB_BUILD")) c->opt_build = (bk[0] == '1') ? 1 : 0;
     if (const char* bp = getenv("TNSB_BUCKET_PASSES")) c->opt_bucket_passes = atoi(bp);
     if (const char* sp = getenv("TNSB_SPECULATE")) c->opt_speculate = atoi(sp) != 0;
+    if (const char* lv = getenv("TNSB_BRICK_LEVEL")) c->opt_force_level = atoi(lv);
     for (int k = 0; k < EV_COUNT; k++) cudaEventCreate(&c->ev[k]);
     *out = c;
     return TNSB_OK;
