@@ -79,8 +79,6 @@ struct BrickArgs {
     unsigned long long* n_neighbors;
     unsigned long long* n_slow;
     int* max_list;            // longest list written (atomicMax): picks the hit column height of the next run
-    int* max_cand;            // march query: largest candidate count of a cell (atomicMax)
-    unsigned long long* n_over8;  // march query: queries of cells with more than 256 candidates (the 8-slot variant sends them to the slow path): picks the register slots of the next run
     int host_out;             // the ragged buffer is mapped host memory: lists leave the SM as aligned, fully coalesced 128-byte stores
     int sort_lists;           // ascending neighbour ids inside every list (the reference's order)
     int* overflow;
@@ -287,9 +285,8 @@ __device__ __forceinline__ void warp_bitonic_sort(int n, int lane, Load ld, Stor
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// slow path: one query, the whole warp, candidates from global memory, count pass + fill pass.  HW = stencil half width in cells
-// (2: half-radius grid of the brick query, 1: cell = r grid of the march query)
-template <bool SYMMETRIC, int HW = 2>
+// slow path: one query, the whole warp, candidates from global memory, count pass + fill pass
+template <bool SYMMETRIC>
 __device__ __noinline__ void brick_slow_query(const BrickArgs& a, float qx, float qy, float qz, int qid, float r2, int cx, int cy, int cz, int lane, unsigned& nb_sum,
                                               uint32_t scratch_a, int scratch_cap)
 {
@@ -299,14 +296,14 @@ __device__ __noinline__ void brick_slow_query(const BrickArgs& a, float qx, floa
     int n_list = 0;
     for (int pass = 0; pass < 2; pass++) {
         int n = 0;
-        for (int dz = -HW; dz <= HW; dz++) {
+        for (int dz = -2; dz <= 2; dz++) {
             const int z = cz + dz;
             if (z < 0 || z >= a.g.nz) continue;
-            for (int dy = -HW; dy <= HW; dy++) {
+            for (int dy = -2; dy <= 2; dy++) {
                 const int y = cy + dy;
                 if (y < 0 || y >= a.g.ny) continue;
                 const uint32_t key0 = ((uint32_t)z * (uint32_t)a.g.ny + (uint32_t)y) * (uint32_t)a.g.nx;
-                const uint32_t lo = a.c.first[key0 + max(cx - HW, 0)], hi = a.c.first[key0 + min(cx + HW + 1, a.g.nx)];
+                const uint32_t lo = a.c.first[key0 + max(cx - 2, 0)], hi = a.c.first[key0 + min(cx + 3, a.g.nx)];
                 for (uint32_t t0 = lo; t0 < hi; t0 += 32) {
                     const uint32_t t = t0 + lane;
                     bool hit = false;

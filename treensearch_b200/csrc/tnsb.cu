@@ -12,7 +12,6 @@
 #include "grid_build.cuh"
 #include "query.cuh"
 #include "query_brick.cuh"
-#include "query_march.cuh"
 #include "shard.cuh"
 
 #include <algorithm>
@@ -76,8 +75,7 @@ struct PairCounters {
     int plan_overflow;
     unsigned long long n_slow;
     int max_list;
-    int max_cand;              // march query: largest candidate count of a cell
-    unsigned long long n_over8; // march query: queries of cells with more than 256 candidates
+    int pad_;
 };
 
 struct SetState {
@@ -164,8 +162,7 @@ struct tnsb_context {
     int opt_point_stride = 3;
     int opt_bucket_passes = 0;          // 0: automatic
     int opt_build = 0;             // 0: bucket build when the cell table is small enough, else radix sort; 1: always radix sort
-    int opt_query_kernel = 0;      // 0: automatic (march query on the row-key grid while its cell table is affordable, else the cell kernel), 1: always the cell kernel, 2: brick query, 3: march query
-    int march_slots = 8;           // candidate register slots of the march query: 8 while the largest neighbourhood of the previous run had <= 256 candidates, else 16
+    int opt_query_kernel = 0;      // 0: automatic (brick query on the half-radius grid while its cell table is affordable, else the cell kernel), 1: always the cell kernel
     int brick_kmax = 128;          // hit column height of the brick query: 128 on the first run, then 64 / 96 while the longest list of the previous run fits
 
     // world box with hysteresis (TreeNSearch.cpp:474-482)
@@ -181,9 +178,7 @@ struct tnsb_context {
     float spec_radius = 0.0f;
     int opt_speculate = 1;
     int opt_force_level = -1;
-    bool brick_mode = false;       // grid built last: linear row keys + prefix tables in `bgrid` (brick / march query) or cell = r + 3-D Morton keys (cell kernel, zsort)
-    bool march_mode = false;       // with brick_mode: cell = r and the march query (else half-radius cells and the brick query)
-    int spec_mode = 0;             // row-key grid kind the speculative grid was built for (1: brick, 2: march)
+    bool brick_mode = false;       // grid built last: half-radius cells + linear row keys (brick query) or cell = r + 3-D Morton keys (cell kernel, zsort)
     BrickGrid bgrid;
 
     DevBuf d_reduce;        // 8 x uint32
@@ -655,77 +650,6 @@ int query_pair_brick(tnsb_context* c, int si, int sj, PairCounters* d_cnt)
     return TNSB_OK;
 }
 
-// ---- march query (query_march.cuh): the same row-key grid with cell = r; candidates in registers, hits as a bit matrix -----------------
-template <int NSLOT, bool VARIABLE, bool SYM>
-cudaError_t launch_march(const BrickArgs& a, int n_sms, cudaStream_t s)
-{
-    typedef MarchSmem<NSLOT, SYM> SM;
-    static_assert(SM::kBytes <= 227 * 1024, "march query variant exceeds the shared memory of an SM");
-    auto kernel = march_query_kernel<NSLOT, VARIABLE, SYM>;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes);
-    if (e != cudaSuccess) return e;
-    kernel<<<n_sms, SM::kWarps * 32, SM::kBytes, s>>>(a);
-    return cudaGetLastError();
-}
-
-int query_pair_march(tnsb_context* c, int si, int sj, PairCounters* d_cnt)
-{
-    auto& qi = c->sets[si];
-    auto& cj = c->sets[sj];
-    PairState& ps = c->pairs[si * c->sets.size() + sj];
-    const bool variable = !c->radius_set;
-    const bool symmetric = variable && c->symmetric;   // TreeNSearch.cpp:2431
-    const BrickGrid& bg = c->bgrid;
-    BrickArgs a;
-    memset(&a, 0, sizeof(a));
-    a.g = bg;
-    a.q = brick_set(qi);
-    a.c = brick_set(cj);
-    a.same_set = si == sj;
-    a.query_limit = c->opt_query_limit >= 0 ? (int)std::min<int64_t>(c->opt_query_limit, INT_MAX) : INT_MAX;
-    a.r2_fixed = c->radius_sq;
-    // one task per chunk of kMarchChunk cells of a row: the plan buffer holds every chunk of the grid, so the plan cannot overflow
-    const int64_t n_chunks = (int64_t)ceil_div(bg.nx, kMarchChunk) * bg.ny * bg.nz;
-    TNSB_CUDA(c, ps.d_tasks.ensure(sizeof(BrickTask) * (size_t)std::max<int64_t>(n_chunks, 1)));
-    ps.max_tasks = (int64_t)(ps.d_tasks.cap / sizeof(BrickTask));
-    a.tasks = ps.d_tasks.as<BrickTask>();
-    a.max_tasks = (uint32_t)std::min<int64_t>(ps.max_tasks, 0x7fffffff);
-    a.n_tasks = &d_cnt->n_tasks;
-    a.plan_overflow = &d_cnt->plan_overflow;
-    a.ticket = &d_cnt->ticket;
-    a.ragged = ps.in_host ? ps.h_ragged.as<int32_t>() : ps.d_ragged.as<int32_t>();
-    a.capacity = ps.capacity;
-    a.list_pos = ps.d_list_pos.as<long long>();
-    a.cursor = &d_cnt->cursor;
-    a.n_neighbors = &d_cnt->n_neighbors;
-    a.n_slow = &d_cnt->n_slow;
-    a.max_list = &d_cnt->max_list;
-    a.max_cand = &d_cnt->max_cand;
-    a.n_over8 = &d_cnt->n_over8;
-    a.host_out = ps.in_host ? 1 : 0;
-    a.sort_lists = c->opt_sort_lists == 1 || (c->opt_sort_lists < 0 && c->opt_host_results) ? 1 : 0;
-    a.overflow = &d_cnt->overflow;
-    cudaStream_t s = c->stream;
-    march_plan_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(n_chunks, 256), 8 * c->n_sms), 256, 0, s>>>(bg, a.q.first, a.tasks, a.max_tasks, a.n_tasks, a.plan_overflow);
-    TNSB_CUDA(c, cudaGetLastError());
-    int slots = c->march_slots;
-    if (c->opt_force_level >= 0) slots = c->opt_force_level == 0 ? 8 : 16;      // TNSB_BRICK_LEVEL: experiments only
-    cudaError_t e;
-    if (slots <= 8) {
-        if (!variable) e = launch_march<8, false, false>(a, c->n_sms, s);
-        else if (!symmetric) e = launch_march<8, true, false>(a, c->n_sms, s);
-        else e = launch_march<8, true, true>(a, c->n_sms, s);
-    } else {
-        if (!variable) e = launch_march<16, false, false>(a, c->n_sms, s);
-        else if (!symmetric) e = launch_march<16, true, false>(a, c->n_sms, s);
-        else e = launch_march<16, true, true>(a, c->n_sms, s);
-    }
-    TNSB_CUDA(c, e);
-    c->stats.n_kernel_launches += 2;
-    c->stats.n_query_launches++;
-    return TNSB_OK;
-}
-
 // prepare_zsort() when the grid of the last run() is still valid (the reference reuses its cells, TreeNSearch.cpp:2598-2661): the
 // sorted records are resident, so no upload, no world box, no bucket build -- only Morton keys of the records and the radix sort
 template <typename Key>
@@ -761,7 +685,7 @@ double ms_since(const std::chrono::steady_clock::time_point& t0)
 }
 
 // upload + world box + grid parameters + sorted grid of every set.  Shared by run() and prepare_zsort().
-int build_grid(tnsb_context* c, GridParams* gp_out, int want_mode /* 0: cell kernel grid, 1: brick query grid, 2: march query grid */, bool need_order)
+int build_grid(tnsb_context* c, GridParams* gp_out, bool want_brick, bool need_order)
 {
     cudaStream_t s = c->stream;
     const int n_sets = (int)c->sets.size();
@@ -817,8 +741,7 @@ int build_grid(tnsb_context* c, GridParams* gp_out, int want_mode /* 0: cell ker
     }
     // ---- steady state: the grid of the previous run is reused WITHOUT waiting for the box (a device-side check decides at the end of
     // the run whether that was legitimate): one host round trip per run() instead of two
-    const bool want_brick = want_mode != 0;
-    if (want_brick && !need_order && c->opt_speculate && c->spec_valid && c->spec_mode == want_mode && c->spec_n_sets == n_sets &&
+    if (want_brick && !need_order && c->opt_speculate && c->spec_valid && c->spec_n_sets == n_sets &&
         (c->radius_set ? c->spec_radius == c->radius : c->spec_radius < 0.0f)) {
         box_check_kernel<<<1, 32, 0, s>>>(c->d_reduce.as<uint32_t>(), c->bgrid, (float)c->r_max, c->radius_set ? 0 : 1, c->d_reduce.as<int>() + 8);
         TNSB_CUDA(c, cudaEventRecord(c->ev[EV_AABB], s));
@@ -826,10 +749,9 @@ int build_grid(tnsb_context* c, GridParams* gp_out, int want_mode /* 0: cell ker
         c->spec_used = true;
         c->stats.speculative_grid = 1;
         c->brick_mode = true;
-        c->march_mode = want_mode == 2;
-        c->stats.cell_size = (float)(c->march_mode ? c->cell : 0.5 * c->cell);
+        c->stats.cell_size = (float)(0.5 * c->cell);
         c->stats.key_bits = 3 * c->bits;
-        c->stats.brick_query = want_mode;
+        c->stats.brick_query = 1;
         for (int d = 0; d < 3; d++) { c->stats.domain_bottom[d] = (float)c->dom_bottom[d]; c->stats.domain_top[d] = (float)c->dom_top[d]; }
         return build_sets_brick(c, c->bgrid);
     }
@@ -893,16 +815,14 @@ int build_grid(tnsb_context* c, GridParams* gp_out, int want_mode /* 0: cell ker
     // ---- brick query grid: half-radius cells over the occupied extent, linear row keys.  Taken while its prefix table (one
     // uint32 per cell and per set) is small next to the point count; huge sparse domains keep the cell kernel + hash.
     c->brick_mode = false;
-    c->march_mode = false;
     c->spec_valid = false;
     if (want_brick && !need_order) {
         BrickGrid bg;
         int64_t dims[3];
-        const bool march = want_mode == 2;
-        bg.inv_cell = (march ? 1.0 : 2.0) / c->cell;
+        bg.inv_cell = 2.0 / c->cell;
         for (int d = 0; d < 3; d++) {
             bg.bottom[d] = c->dom_bottom[d];
-            dims[d] = (int64_t)std::floor(((double)hi[d] - bg.bottom[d]) * bg.inv_cell) + 1 + (march ? 2 : 4);      // + 2 r: room for the cloud to move while the grid is reused
+            dims[d] = (int64_t)std::floor(((double)hi[d] - bg.bottom[d]) * bg.inv_cell) + 1 + 4;      // + 4 cells (2 r): room for the cloud to move while the grid is reused
         }
         int64_t n_max = 0;
         for (auto& st : c->sets) n_max = std::max<int64_t>(n_max, st.n);
@@ -911,13 +831,11 @@ int build_grid(tnsb_context* c, GridParams* gp_out, int want_mode /* 0: cell ker
             bg.nx = (int)dims[0]; bg.ny = (int)dims[1]; bg.nz = (int)dims[2];
             c->bgrid = bg;
             c->brick_mode = true;
-            c->march_mode = march;
             c->spec_valid = true;
-            c->spec_mode = want_mode;
             c->spec_n_sets = n_sets;
             c->spec_radius = c->radius_set ? c->radius : -1.0f;
-            c->stats.cell_size = (float)(march ? c->cell : 0.5 * c->cell);
-            c->stats.brick_query = want_mode;
+            c->stats.cell_size = (float)(0.5 * c->cell);
+            c->stats.brick_query = 1;
             return build_sets_brick(c, bg);
         }
     }
@@ -952,7 +870,7 @@ int run_impl(tnsb_context* c)
     GridParams gp;
     memset(&gp, 0, sizeof(gp));
     if (n_total > 0) {
-        rc = build_grid(c, &gp, c->opt_query_kernel == 1 ? 0 : (c->opt_query_kernel == 2 ? 1 : 2), false);
+        rc = build_grid(c, &gp, c->opt_query_kernel == 0, false);
         if (rc != TNSB_OK) return rc;
     } else {
         for (int k = 0; k < EV_COUNT; k++) TNSB_CUDA(c, cudaEventRecord(c->ev[k], s));
@@ -970,8 +888,7 @@ int run_impl(tnsb_context* c)
     PairCounters* h_out = h_init + std::max<size_t>(n_pairs, 1);
     const int qlimit = c->opt_query_limit >= 0 ? (int)std::min<int64_t>(c->opt_query_limit, INT_MAX) : INT_MAX;
 
-    int brick_max_list = 0, march_max_cand = 0;
-    int64_t march_over8 = 0, march_queries = 0;
+    int brick_max_list = 0;
     std::vector<int> todo;
     for (int id : act) {
         const int si = id / n_sets;
@@ -1006,8 +923,7 @@ int run_impl(tnsb_context* c)
             TNSB_CUDA(c, cudaMemcpyAsync(c->d_counters.as<PairCounters>() + id, h_init + id, sizeof(PairCounters), cudaMemcpyHostToDevice, s));
         for (int id : todo) {
             const int si = id / n_sets, sj = id % n_sets;
-            if (c->march_mode) rc = query_pair_march(c, si, sj, c->d_counters.as<PairCounters>() + id);
-            else if (c->brick_mode) rc = query_pair_brick(c, si, sj, c->d_counters.as<PairCounters>() + id);
+            if (c->brick_mode) rc = query_pair_brick(c, si, sj, c->d_counters.as<PairCounters>() + id);
             else rc = c->key64 ? query_pair<uint64_t>(c, si, sj, gp, c->d_counters.as<PairCounters>() + id)
                                : query_pair<uint32_t>(c, si, sj, gp, c->d_counters.as<PairCounters>() + id);
             if (rc != TNSB_OK) return rc;
@@ -1031,10 +947,7 @@ int run_impl(tnsb_context* c)
             PairState& ps = c->pairs[id];
             const PairCounters& r = h_out[id];
             c->stats.n_slow_queries += (int64_t)r.n_slow;
-            brick_max_list = std::max(brick_max_list, (r.n_slow > 0 && !c->march_mode) ? 1000 : r.max_list);
-            march_max_cand = std::max(march_max_cand, r.max_cand);
-            march_over8 += (int64_t)r.n_over8;
-            march_queries += ps.n_lists;
+            brick_max_list = std::max(brick_max_list, r.n_slow > 0 ? 1000 : r.max_list);
             if (r.plan_overflow) {
                 // the planner kept counting: n_tasks is the exact number of bricks
                 ps.max_tasks = (int64_t)r.n_tasks + 1024;
@@ -1061,10 +974,7 @@ int run_impl(tnsb_context* c)
         todo.swap(again);
     }
     // hit column height of the next run: the short columns (more warps per SM) while the longest list leaves some headroom
-    if (c->brick_mode && !c->march_mode && !act.empty()) c->brick_kmax = brick_max_list <= 62 ? 64 : (brick_max_list <= 92 ? 96 : 128);
-    // register slots of the next march query: 8 while every neighbourhood of this run would have fitted them
-    // (16 slots cost registers and shared memory, i.e. resident warps: taken when more than 0.5 % of the queries sit in cells that overflow 8)
-    if (c->march_mode && !act.empty()) c->march_slots = (march_over8 * 200 <= march_queries) ? 8 : 16;
+    if (c->brick_mode && !act.empty()) c->brick_kmax = brick_max_list <= 62 ? 64 : (brick_max_list <= 92 ? 96 : 128);
     c->stats.max_list = brick_max_list;
     if (c->opt_sort_lists == 1 && !c->brick_mode) {
         for (int id : act) {
@@ -1168,7 +1078,7 @@ int tnsb_create(tnsb_context** out, int device)
         return TNSB_ERR_CUDA;
     }
     c->own_stream = c->stream;
-    if (const char* qk = getenv("TNSB_QUERY_KERNEL")) c->opt_query_kernel = (qk[0] >= '0' && qk[0] <= '3') ? qk[0] - '0' : 0;      // A/B switches for tests and profiling
+    if (const char* qk = getenv("TNSB_QUERY_KERNEL")) c->opt_query_kernel = (qk[0] == '0') ? 0 : 1;      // A/B switches for tests and profiling
     if (const char* bk = getenv("TNSB_BUILD")) c->opt_build = (bk[0] == '1') ? 1 : 0;
     if (const char* bp = getenv("TNSB_BUCKET_PASSES")) c->opt_bucket_passes = atoi(bp);
     if (const char* sp = getenv("TNSB_SPECULATE")) c->opt_speculate = atoi(sp) != 0;
@@ -1347,7 +1257,7 @@ int tnsb_set_option(tnsb_context* c, int option, int64_t value)
         if (value != 0 && value != 1) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: build must be 0 (automatic) or 1 (radix sort).");
         c->opt_build = (int)value; return TNSB_OK;
     case TNSB_OPT_QUERY_KERNEL:
-        if (value < 0 || value > 3) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: query kernel must be 0 (automatic: march query), 1 (cell kernel), 2 (brick query) or 3 (march query).");
+        if (value != 0 && value != 1) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: query kernel must be 0 (automatic: brick query) or 1 (cell kernel).");
         c->opt_query_kernel = (int)value; return TNSB_OK;
     case TNSB_OPT_POINT_STRIDE:
         if (value != 3 && value != 4) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: point stride must be 3 (xyz) or 4 (xyz + id).");
@@ -1443,7 +1353,7 @@ int tnsb_prepare_zsort(tnsb_context* c)
         // row-key order): the order handed to the user is the libmorton Z-order, stable inside a cell, so radix sort by Morton keys now
         GridParams gp;
         memset(&c->stats, 0, sizeof(c->stats));
-        rc = build_grid(c, &gp, 0, true);
+        rc = build_grid(c, &gp, false, true);
         if (rc != TNSB_OK) return rc;
     }
     for (auto& st : c->sets) {
