@@ -285,41 +285,56 @@ __device__ __forceinline__ void warp_bitonic_sort(int n, int lane, Load ld, Stor
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// slow path: one query, the whole warp, candidates from global memory, count pass + fill pass
+// slow path: one query, the whole warp, candidates from global memory.  The 25 row bounds are fetched by 25 lanes at once, the rows are
+// walked with FOUR warp-wide candidate loads in flight (the path is bound by memory latency, not by arithmetic), and the hits of the
+// first pass are kept in the warp's scratch: a list that fits it (<= scratch_cap ids) is written out -- sorted if asked -- without a second
+// pass; longer lists take a second pass straight into the ragged buffer.
 template <bool SYMMETRIC>
 __device__ __noinline__ void brick_slow_query(const BrickArgs& a, float qx, float qy, float qz, int qid, float r2, int cx, int cy, int cz, int lane, unsigned& nb_sum,
                                               uint32_t scratch_a, int scratch_cap)
 {
     const unsigned lt = lanemask_lt();
+    uint32_t lo = 0, hi = 0;
+    if (lane < 25) {
+        const int y = cy + lane % 5 - 2, z = cz + lane / 5 - 2;
+        if (y >= 0 && y < a.g.ny && z >= 0 && z < a.g.nz) {
+            const uint32_t key0 = ((uint32_t)z * (uint32_t)a.g.ny + (uint32_t)y) * (uint32_t)a.g.nx;
+            lo = a.c.first[key0 + max(cx - 2, 0)];
+            hi = a.c.first[key0 + min(cx + 3, a.g.nx)];
+        }
+    }
     int32_t* dst = nullptr;
-    bool to_scratch = false;
     int n_list = 0;
     for (int pass = 0; pass < 2; pass++) {
         int n = 0;
-        for (int dz = -2; dz <= 2; dz++) {
-            const int z = cz + dz;
-            if (z < 0 || z >= a.g.nz) continue;
-            for (int dy = -2; dy <= 2; dy++) {
-                const int y = cy + dy;
-                if (y < 0 || y >= a.g.ny) continue;
-                const uint32_t key0 = ((uint32_t)z * (uint32_t)a.g.ny + (uint32_t)y) * (uint32_t)a.g.nx;
-                const uint32_t lo = a.c.first[key0 + max(cx - 2, 0)], hi = a.c.first[key0 + min(cx + 3, a.g.nx)];
-                for (uint32_t t0 = lo; t0 < hi; t0 += 32) {
-                    const uint32_t t = t0 + lane;
-                    bool hit = false;
-                    int id = -1;
-                    if (t < hi) {
-                        const float4 v = a.c.pts[t];
-                        id = __float_as_int(v.w);
-                        const float d2 = dist2(qx, qy, qz, v.x, v.y, v.z);
-                        hit = d2 <= r2;
-                        if (SYMMETRIC) hit = hit || (d2 <= a.c.r2[t]);
-                        if (a.same_set && id == qid) hit = false;
+        for (int row = 0; row < 25; row++) {
+            const uint32_t lo_r = __shfl_sync(kFull, lo, row), hi_r = __shfl_sync(kFull, hi, row);
+            for (uint32_t t0 = lo_r; t0 < hi_r; t0 += 128u) {
+                float4 v[4];
+                float w[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t t = t0 + 32u * u + (uint32_t)lane;
+                    v[u] = make_float4(3.0e38f, 0.0f, 0.0f, __int_as_float(-1));
+                    w[u] = -1.0f;
+                    if (t < hi_r) {
+                        v[u] = a.c.pts[t];
+                        if (SYMMETRIC) w[u] = a.c.r2[t];
                     }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (t0 + 32u * u >= hi_r) break;
+                    const int id = __float_as_int(v[u].w);
+                    const float d2 = dist2(qx, qy, qz, v[u].x, v[u].y, v[u].z);
+                    bool hit = d2 <= r2;
+                    if (SYMMETRIC) hit = hit || (d2 <= w[u]);
+                    if (a.same_set && id == qid) hit = false;
                     const unsigned m = __ballot_sync(kFull, hit);
-                    if (pass == 1 && hit) {
-                        if (to_scratch) sts_u32(scratch_a + (uint32_t)(n + __popc(m & lt)) * 4u, (uint32_t)id);
-                        else dst[1 + n + __popc(m & lt)] = id;
+                    if (hit) {
+                        const int k = n + __popc(m & lt);
+                        if (pass == 1) dst[1 + k] = id;
+                        else if (k < scratch_cap) sts_u32(scratch_a + (uint32_t)k * 4u, (uint32_t)id);
                     }
                     n += __popc(m);
                 }
@@ -341,21 +356,22 @@ __device__ __noinline__ void brick_slow_query(const BrickArgs& a, float qx, floa
             }
             nb_sum += (unsigned)n;
             n_list = n;
-            to_scratch = a.sort_lists && n <= scratch_cap;      // ascending ids: the list is sorted in shared memory before it leaves the SM
+            if (n <= scratch_cap) {
+                // the whole list sits in the scratch: sort it there, one coalesced copy, done
+                __syncwarp();
+                if (a.sort_lists && n > 1)
+                    warp_bitonic_sort(n, lane, [&](int i) { return (int)lds_u32(scratch_a + (uint32_t)i * 4u); }, [&](int i, int x) { sts_u32(scratch_a + (uint32_t)i * 4u, (uint32_t)x); });
+                for (int i = lane; i < n; i += 32) dst[1 + i] = (int)lds_u32(scratch_a + (uint32_t)i * 4u);
+                __syncwarp();
+                return;
+            }
         }
     }
     if (a.sort_lists && n_list > 1) {
+        // longer than the warp's scratch (thousands of neighbours): in place, in the ragged buffer
         __syncwarp();
-        if (to_scratch) {
-            warp_bitonic_sort(n_list, lane, [&](int i) { return (int)lds_u32(scratch_a + (uint32_t)i * 4u); }, [&](int i, int v) { sts_u32(scratch_a + (uint32_t)i * 4u, (uint32_t)v); });
-            for (int i = lane; i < n_list; i += 32) dst[1 + i] = (int)lds_u32(scratch_a + (uint32_t)i * 4u);
-        } else {
-            // longer than the warp's scratch (thousands of neighbours): in place, in global memory
-            volatile int32_t* v = dst + 1;
-            warp_bitonic_sort(n_list, lane, [&](int i) { return (int)v[i]; }, [&](int i, int x) { v[i] = x; });
-        }
-    } else if (to_scratch && n_list == 1) {
-        if (lane == 0) dst[1] = (int)lds_u32(scratch_a);
+        volatile int32_t* v = dst + 1;
+        warp_bitonic_sort(n_list, lane, [&](int i) { return (int)v[i]; }, [&](int i, int x) { v[i] = x; });
     }
 }
 
