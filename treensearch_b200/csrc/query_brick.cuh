@@ -93,7 +93,7 @@ struct BrickSmem {
     static constexpr int kOffT = kOffR2 + (SYM ? (SLAB + kDummy) * 4 : 0);
     static constexpr int kOffMeta = kOffT + ((kSlabRows * kTW * 2 + 15) & ~15);
     // meta words: [0] x0 [1] y0 [2] z0 [3] dims | flags [4] n queries [5] staged [6] next warp task [7] end
-    //             [8, 24) qs   [24, 41) qoff   [44, 60) qdelta
+    //             [8, 24) qs   [24, 41) qoff   [41] queries per warp task   [44, 60) qdelta
     static constexpr int kMetaWords = 64;
     static constexpr int kOffRowKey = kOffMeta + kMetaWords * 4;        // producer scratch: key of the first cell of every slab row
     static constexpr int kOffRowBase = kOffRowKey + kSlabRows * 4;      //                   slab position - global position of the row's records
@@ -547,6 +547,12 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
             if (lane == 0) {
                 meta[0] = (uint32_t)x0; meta[1] = (uint32_t)y0; meta[2] = (uint32_t)z0; meta[3] = bt.dims;
                 meta[4] = nq_all; meta[5] = staged ? 1u : 0u; meta[6] = 0u; meta[7] = 0u;
+                // queries per warp task: 32 -- or, for a brick with few queries and a heavy slab (dense neighbourhoods: long walks, lists
+                // that overflow into the warp-cooperative paths), as few as it takes to give every consumer warp a share of the brick:
+                // only two bricks are in flight per SM, so a brick that is one task would leave all other consumer warps idle
+                uint32_t tq = 32u;
+                if ((slow_brick || (total >= 1024u && total >= 8u * nq_all)) && nq_all < 32u * (uint32_t)NCONS) tq = max((nq_all + (uint32_t)NCONS - 1u) / (uint32_t)NCONS, 1u);
+                meta[41] = tq;
             }
             __syncwarp();
             if (lane < kQRows) meta[44 + lane] = (uint32_t)s_rowbase[((lane >> 2) + 2) * kRowPitch + (lane & 3) + 2];
@@ -564,14 +570,15 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
                     bulk_g2s(buf_a + SM::kOffSlab + ro[h] * 16u, a.c.pts + g0[h], len[h] * 16u, full);
                 }
                 if (SYMMETRIC) {
-                    // r^2 of the rows' records: plain coalesced loads, one row per iteration (4-byte elements have no 16-byte
-                    // alignment to offer a bulk copy)
+                    // r^2 of the rows' records (4-byte elements have no 16-byte alignment to offer a bulk copy): 4-byte asynchronous copies,
+                    // all of them in flight at once; the producer waits for them once, right before its arrival on `full`
                     float* const sr2 = reinterpret_cast<float*>(buf + SM::kOffR2);
 #pragma unroll 4
                     for (int r = 0; r < kSlabRows; r++) {
                         const uint32_t lr = __shfl_sync(kFull, len[r >> 5], r & 31), gr = __shfl_sync(kFull, g0[r >> 5], r & 31), rr_ = __shfl_sync(kFull, ro[r >> 5], r & 31);
-                        for (uint32_t k = lane; k < lr; k += 32) sr2[rr_ + k] = a.c.r2[gr + k];
+                        for (uint32_t k = lane; k < lr; k += 32) cp_async_4(sr2 + rr_ + k, a.c.r2 + gr + k);
                     }
+                    cp_async_commit();
                 }
                 // T[row][i] = slab position of the first record of cell x0 - 2 + i of that row: one row per load instruction (lane = i),
                 // sixteen rows in flight
@@ -598,6 +605,7 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
                     }
                 }
             }
+            if (SYMMETRIC) cp_async_wait_all();
             __syncwarp();
             if (lane == 0) mbar_arrive(full);
         }
@@ -627,15 +635,16 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
             const int ex = (int)(meta[3] & 0xffu);
             const bool staged = meta[5] != 0u;
             const int nq = (int)meta[4];
+            const int tqs = (int)meta[41];
             const uint32_t slab_a = buf_a + SM::kOffSlab;
 
             for (;;) {
                 int wt = 0;
                 if (lane == 0) wt = (int)atomicAdd(&meta[6], 1u);
                 wt = __shfl_sync(kFull, wt, 0);
-                if (wt * 32 >= nq) break;
-                const int ci = wt * 32 + lane;
-                const bool has = ci < nq;
+                if (wt * tqs >= nq) break;
+                const int ci = wt * tqs + lane;
+                const bool has = lane < tqs && ci < nq;
                 // query row of this lane: last row whose first query is <= ci (binary search over the 16 row offsets)
                 int rr = (ci >= (int)meta[24 + 8]) ? 8 : 0;
                 rr += (ci >= (int)meta[24 + rr + 4]) ? 4 : 0;
