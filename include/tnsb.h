@@ -99,6 +99,8 @@ typedef struct tnsb_stats {
     int64_t n_slow_queries;      /* brick query: queries answered by its warp-cooperative slow path (dense cells, long lists) */
     int32_t max_list;            /* brick query: longest neighbour list of the last run (1000: some list overflowed its column) */
     int32_t speculative_grid;    /* 1: the last run reused the previous run's grid without waiting for the world box (checked on the device) */
+    int32_t graph_replay;        /* 1: the enqueue phase of the last run was ONE CUDA graph launch (small problems in steady state; per-stage timings are 0,
+                                    ms_total_device spans the whole graph).  TNSB_GRAPH=0 in the environment disables it */
 } tnsb_stats;
 
 /* ---- life cycle --------------------------------------------------------------------------------------------------- */

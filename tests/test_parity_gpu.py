@@ -618,6 +618,70 @@ def test_speculative_grid_reuse_and_fallback(tnsb):
     assert_matches_port(e2, dict(sets=[(pts, rad)], radius=None, pairs=[(0, 0)], symmetric=True))
 
 
+def test_graph_replay_small_steady_state(tnsb):
+    """Small problems in steady state: the enqueue phase of run() becomes ONE CUDA graph launch (captured once two consecutive runs
+    looked alike, replayed while configuration / pointers / sizes / buffers are unchanged).  Moving points, host and device arrays,
+    two sets with variable radii; anything that changes the key -- or a cloud that leaves the reused grid -- falls back to a plain run."""
+    import torch
+    rs = np.random.RandomState(11)
+    base = (rs.random_sample((20_000, 3)) * 2.0).astype(np.float32)
+    r = 0.09
+    for device_resident in (False, True):
+        pts = base.copy()
+        arr = torch.from_numpy(pts).cuda() if device_resident else pts
+        eng = tnsb.TreeNSearch()
+        eng.set_search_radius(r)
+        eng.add_point_set(arr)
+        eng.set_active_search(0, 0, True)
+        replays = 0
+        for step in range(7):
+            pts += np.float32(0.002)                             # the host array moves in place; the device copy follows it
+            if device_resident:
+                arr.copy_(torch.from_numpy(pts))
+            eng.run()
+            st = eng.stats()
+            replays += st["graph_replay"]
+            if step >= 4:
+                assert st["graph_replay"] == 1 and st["speculative_grid"] == 1, (device_resident, step, st)
+            assert_matches_port(eng, dict(sets=[(pts, None)], radius=r, pairs=[(0, 0)], symmetric=True))
+        assert replays >= 3
+        pts[:500] += np.float32(0.9)                             # a splash outside the reused grid: the graph run is void and repeats itself
+        if device_resident:
+            arr.copy_(torch.from_numpy(pts))
+        eng.run()
+        st = eng.stats()
+        assert st["n_reruns"] >= 1 and st["graph_replay"] == 0
+        assert_matches_port(eng, dict(sets=[(pts, None)], radius=r, pairs=[(0, 0)], symmetric=True))
+        for _ in range(4):
+            eng.run()
+        assert eng.stats()["graph_replay"] == 1                  # captured again for the new grid
+        eng.set_active_search(0, 0, False)                       # a change of the configuration changes the key
+        eng.run()
+        assert eng.stats()["graph_replay"] == 0 and eng.stats()["n_neighbors"] == 0
+        eng.set_active_search(0, 0, True)
+        eng.run()
+        assert_matches_port(eng, dict(sets=[(pts, None)], radius=r, pairs=[(0, 0)], symmetric=True))
+    # two sets, variable radii, three pairs
+    case = cases.GOLDEN_CASES["variable_random_sym"]()
+    eng = run_engine(tnsb, case)
+    for _ in range(5):
+        eng.run()
+    assert eng.stats()["graph_replay"] == 1
+    assert_matches_port(eng, case)
+    # switched off
+    eng = run_engine(tnsb, case)
+    import os
+    os.environ["TNSB_GRAPH"] = "0"
+    try:
+        e2 = run_engine(tnsb, case)
+        for _ in range(4):
+            e2.run()
+        assert e2.stats()["graph_replay"] == 0
+        assert_matches_port(e2, case)
+    finally:
+        del os.environ["TNSB_GRAPH"]
+
+
 def test_resize_fast_path_keeps_grid(tnsb):
     """resize_point_set with the same pointer and size is a no-op (TreeNSearch.cpp:77-79, :107-109): the grid stays valid for prepare_zsort."""
     import torch

@@ -39,7 +39,7 @@ class Stats(C.Structure):
         ("n_cells", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("n_kernel_launches", C.c_int32), ("n_query_launches", C.c_int32), ("key_bits", C.c_int32), ("sort_passes", C.c_int32),
         ("n_reruns", C.c_int32), ("cell_size", C.c_float), ("domain_bottom", C.c_float * 3), ("domain_top", C.c_float * 3),
-        ("brick_query", C.c_int32), ("n_slow_queries", C.c_int64), ("max_list", C.c_int32), ("speculative_grid", C.c_int32),
+        ("brick_query", C.c_int32), ("n_slow_queries", C.c_int64), ("max_list", C.c_int32), ("speculative_grid", C.c_int32), ("graph_replay", C.c_int32),
     ]
 
     def as_dict(self):

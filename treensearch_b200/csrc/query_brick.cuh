@@ -660,6 +660,7 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
                 }
                 const int qid = __float_as_int(q.w);
                 const bool active = has && qid < query_limit;
+                if (!__any_sync(kFull, active)) continue;          // a task of find-only points (the halo layers of a Z-slab shard)
                 double tx, ty, tz;
                 const int cx = brick_cell(q.x, g.bottom[0], g.inv_cell, g.nx, tx);
                 (void)brick_cell(q.y, g.bottom[1], g.inv_cell, g.ny, ty);

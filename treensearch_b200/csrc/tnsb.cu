@@ -31,12 +31,16 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// bumped by every (re)allocation of an engine buffer: a captured CUDA graph of run() carries raw pointers and is void afterwards
+static unsigned long long g_alloc_epoch = 0;
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     cudaError_t ensure(size_t bytes, double headroom = 1.0)
     {
         if (bytes <= cap) return cudaSuccess;
+        g_alloc_epoch++;
         if (p) { cudaFree(p); p = nullptr; cap = 0; }
         const size_t want = (size_t)((double)bytes * headroom) + 256;
         cudaError_t e = cudaMalloc(&p, want);
@@ -54,6 +58,7 @@ struct PinBuf {
     cudaError_t ensure(size_t bytes, double headroom = 1.0)
     {
         if (bytes <= cap) return cudaSuccess;
+        g_alloc_epoch++;
         if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
         const size_t want = (size_t)((double)bytes * headroom) + 256;
         cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
@@ -89,6 +94,7 @@ struct SetState {
     int n = 0;
     // device state
     DevBuf up_pts, up_radii;       // uploaded raw arrays (when the user arrays live on the host)
+    PinBuf hs_pts, hs_radii;       // small pageable host arrays pass through a pinned staging copy (graph replay needs a fixed, pinned source)
     DevBuf cv_pts, cv_radii;       // float conversions of double arrays
     const float* d_pts = nullptr;  // float xyz actually used by the kernels
     const float* d_radii = nullptr;
@@ -177,6 +183,17 @@ struct tnsb_context {
     int spec_n_sets = 0;
     float spec_radius = 0.0f;
     int opt_speculate = 1;
+    // CUDA graph of the steady-state run() of a SMALL problem (launch-latency bound: ~20 kernels and copies per run): captured once two
+    // consecutive runs had the same key (configuration, pointers, sizes, buffers), replayed while the key holds
+    int opt_graph = 1;
+    cudaGraphExec_t graph_exec = nullptr;
+    std::vector<uint64_t> graph_key, last_key;
+    std::vector<int> graph_act;
+    tnsb_stats graph_stats;
+    struct HostCopy { void* dst; const void* src; size_t bytes; };
+    std::vector<HostCopy> graph_host_copies, cur_host_copies;
+    bool capturing = false;        // stream capture in progress: no event records, no synchronisation
+    bool graph_run = false;        // this run went through the graph: per-stage timings are not available
     int opt_force_level = -1;
     bool brick_mode = false;       // grid built last: half-radius cells + linear row keys (brick query) or cell = r + 3-D Morton keys (cell kernel, zsort)
     BrickGrid bgrid;
@@ -216,6 +233,12 @@ int fail(tnsb_context* c, int code, const std::string& msg)
         }                                                                                                    \
     } while (0)
 
+// stage events are not recorded while run() is being captured into a graph
+#define TNSB_EVENT(c, call)                     \
+    do {                                        \
+        if (!(c)->capturing) TNSB_CUDA(c, call); \
+    } while (0)
+
 // makes the context's device current for one entry point and restores the caller's device on every exit path
 struct DeviceGuard {
     int prev = -1, dev;
@@ -245,11 +268,22 @@ bool is_pinned_pointer(const void* p)
 }
 
 // makes `src` (host or device) available on the device; returns the device pointer in *out
-int stage_input(tnsb_context* c, const void* src, size_t bytes, DevBuf& up, const void** out)
+int stage_input(tnsb_context* c, const void* src, size_t bytes, DevBuf& up, PinBuf& hs, const void** out)
 {
     if (bytes == 0 || !src) { *out = nullptr; return TNSB_OK; }
     if (is_device_pointer(src)) { *out = src; return TNSB_OK; }
     TNSB_CUDA(c, up.ensure(bytes, 1.1));
+    if (bytes < ((size_t)4 << 20) && !is_pinned_pointer(src)) {
+        // small pageable array: through a pinned staging copy (one host memcpy), so that the upload is a plain pinned copy --
+        // also the form a captured graph can replay
+        TNSB_CUDA(c, hs.ensure(bytes, 1.25));
+        memcpy(hs.p, src, bytes);
+        c->cur_host_copies.push_back({ hs.p, src, bytes });
+        TNSB_CUDA(c, cudaMemcpyAsync(up.p, hs.p, bytes, cudaMemcpyHostToDevice, c->stream));
+        c->stats.h2d_bytes += (int64_t)bytes;
+        *out = up.p;
+        return TNSB_OK;
+    }
     // registration pays from a few MB on (it costs ~0.2 ms per MB once; a pageable copy runs at ~12 GB/s every run)
     if (c->opt_pin_user && bytes >= ((size_t)4 << 20) && !is_pinned_pointer(src)) {
         auto it = c->registered.find(src);
@@ -324,7 +358,7 @@ int build_sets(tnsb_context* c, const GridParams& gp, bool need_order, const int
         }
         launches++;
     }
-    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_KEYS], s));
+    TNSB_EVENT(c, cudaEventRecord(c->ev[EV_KEYS], s));
     // ---- sort: exclusive scan of the cell populations (bucket) / radix sort of (key, index)
     for (auto& st : c->sets) {
         if (st.n == 0) continue;
@@ -344,7 +378,7 @@ int build_sets(tnsb_context* c, const GridParams& gp, bool need_order, const int
             st.order_valid = true;
         }
     }
-    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_SORT], s));
+    TNSB_EVENT(c, cudaEventRecord(c->ev[EV_SORT], s));
     // ---- reorder: scatter into the cells (bucket) / gather through the sorted permutation (radix)
     for (auto& st : c->sets) {
         if (st.n == 0) continue;
@@ -364,7 +398,7 @@ int build_sets(tnsb_context* c, const GridParams& gp, bool need_order, const int
                                                               st.sorted.as<float4>(), st.sorted_r2.as<float>());
         launches++;
     }
-    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_REORDER], s));
+    TNSB_EVENT(c, cudaEventRecord(c->ev[EV_REORDER], s));
     // ---- occupied cells: count, scan, (one sync for the cell counts), emit + lookup structure
     TNSB_CUDA(c, c->d_misc.ensure(sizeof(uint32_t) * (size_t)std::max(n_sets, 1)));
     for (int si = 0; si < n_sets; si++) {
@@ -441,7 +475,7 @@ int build_sets(tnsb_context* c, const GridParams& gp, bool need_order, const int
         }
         st.sorted_valid = true;
     }
-    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_CELLS], s));
+    TNSB_EVENT(c, cudaEventRecord(c->ev[EV_CELLS], s));
     TNSB_CUDA(c, cudaGetLastError());
     return TNSB_OK;
 }
@@ -528,7 +562,7 @@ int build_sets_brick(tnsb_context* c, const BrickGrid& bg)
         brick_keygen_count_kernel<<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.n, st.d_stride, bg, st.keys[0].as<uint32_t>(), st.first.as<uint32_t>());
         launches++;
     }
-    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_KEYS], s));
+    TNSB_EVENT(c, cudaEventRecord(c->ev[EV_KEYS], s));
     for (auto& st : c->sets) {
         if (st.n == 0) continue;
         uint32_t* first = st.first.as<uint32_t>();
@@ -536,7 +570,7 @@ int build_sets_brick(tnsb_context* c, const BrickGrid& bg)
         TNSB_CUDA(c, cudaMemcpyAsync(st.cursor.p, first, sizeof(uint32_t) * (size_t)n_keys, cudaMemcpyDeviceToDevice, s));
         c->stats.sort_passes = std::max(c->stats.sort_passes, 1);
     }
-    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_SORT], s));
+    TNSB_EVENT(c, cudaEventRecord(c->ev[EV_SORT], s));
     for (auto& st : c->sets) {
         if (st.n == 0) continue;
         TNSB_CUDA(c, st.sorted.ensure(sizeof(float4) * (size_t)st.n, 1.1));
@@ -550,8 +584,8 @@ int build_sets_brick(tnsb_context* c, const BrickGrid& bg)
         launches += passes;
         st.sorted_valid = true;
     }
-    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_REORDER], s));
-    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_CELLS], s));
+    TNSB_EVENT(c, cudaEventRecord(c->ev[EV_REORDER], s));
+    TNSB_EVENT(c, cudaEventRecord(c->ev[EV_CELLS], s));
     TNSB_CUDA(c, cudaGetLastError());
     return TNSB_OK;
 }
@@ -691,7 +725,7 @@ int build_grid(tnsb_context* c, GridParams* gp_out, bool want_brick, bool need_o
     const int n_sets = (int)c->sets.size();
     TNSB_CUDA(c, c->h_small.ensure(4096));
     TNSB_CUDA(c, c->d_reduce.ensure(64));
-    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_BEGIN], s));
+    TNSB_EVENT(c, cudaEventRecord(c->ev[EV_BEGIN], s));
     c->spec_used = false;
 
     // ---- upload (or adopt device pointers)
@@ -706,12 +740,12 @@ int build_grid(tnsb_context* c, GridParams* gp_out, bool want_brick, bool need_o
         const void* ur = st.is_f64 ? (const void*)st.u_radii_f64 : (const void*)st.u_radii_f32;
         if (st.n > 0 && !up) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: point set " + std::to_string(si) + " has a null coordinate pointer.");
         if (st.n > 0 && st.has_radii && !ur) return fail(c, TNSB_ERR_INVALID_ARGUMENT, "tnsb: point set " + std::to_string(si) + " has a null radii pointer.");
-        int rc = stage_input(c, up, esz * stride * (size_t)st.n, st.up_pts, &raw_pts[si]);
+        int rc = stage_input(c, up, esz * stride * (size_t)st.n, st.up_pts, st.hs_pts, &raw_pts[si]);
         if (rc != TNSB_OK) return rc;
-        rc = stage_input(c, st.has_radii ? ur : nullptr, esz * (size_t)st.n, st.up_radii, &raw_radii[si]);
+        rc = stage_input(c, st.has_radii ? ur : nullptr, esz * (size_t)st.n, st.up_radii, st.hs_radii, &raw_radii[si]);
         if (rc != TNSB_OK) return rc;
     }
-    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_UPLOAD], s));
+    TNSB_EVENT(c, cudaEventRecord(c->ev[EV_UPLOAD], s));
 
     // ---- world box + radius range (and double -> float conversion)
     uint32_t* h_red = c->h_small.as<uint32_t>();
@@ -744,7 +778,7 @@ int build_grid(tnsb_context* c, GridParams* gp_out, bool want_brick, bool need_o
     if (want_brick && !need_order && c->opt_speculate && c->spec_valid && c->spec_n_sets == n_sets &&
         (c->radius_set ? c->spec_radius == c->radius : c->spec_radius < 0.0f)) {
         box_check_kernel<<<1, 32, 0, s>>>(c->d_reduce.as<uint32_t>(), c->bgrid, (float)c->r_max, c->radius_set ? 0 : 1, c->d_reduce.as<int>() + 8);
-        TNSB_CUDA(c, cudaEventRecord(c->ev[EV_AABB], s));
+        TNSB_EVENT(c, cudaEventRecord(c->ev[EV_AABB], s));
         c->stats.n_kernel_launches++;
         c->spec_used = true;
         c->stats.speculative_grid = 1;
@@ -756,7 +790,7 @@ int build_grid(tnsb_context* c, GridParams* gp_out, bool want_brick, bool need_o
         return build_sets_brick(c, c->bgrid);
     }
     TNSB_CUDA(c, cudaMemcpyAsync(h_red + 16, c->d_reduce.p, 32, cudaMemcpyDeviceToHost, s));
-    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_AABB], s));
+    TNSB_EVENT(c, cudaEventRecord(c->ev[EV_AABB], s));
     TNSB_CUDA(c, cudaStreamSynchronize(s));
     h_red += 8;                                          // the results sit at h_red[8 .. 15] below
     float lo[3], hi[3];
@@ -851,87 +885,199 @@ float ev_ms(tnsb_context* c, int a, int b)
 
 int run_impl(tnsb_context* c);
 
+// Everything the work enqueued by a steady-state run() depends on: configuration, borrowed pointers, sizes, the reused grid, every
+// engine buffer (through the allocation epoch).  Two runs with the same key enqueue the same kernels with the same arguments.
+std::vector<uint64_t> make_run_key(const tnsb_context* c)
+{
+    std::vector<uint64_t> k;
+    auto f = [&](double v) { uint64_t u; memcpy(&u, &v, 8); k.push_back(u); };
+    k.push_back((uint64_t)(uintptr_t)c->stream);
+    k.push_back((uint64_t)c->device);
+    k.push_back(g_alloc_epoch);
+    k.push_back((uint64_t)c->sets.size());
+    k.push_back((uint64_t)c->radius_set | ((uint64_t)c->symmetric << 1) | ((uint64_t)c->opt_host_results << 2) | ((uint64_t)c->opt_pin_user << 3) |
+                ((uint64_t)c->opt_zero_copy << 4) | ((uint64_t)c->spec_valid << 5) | ((uint64_t)c->domain_valid << 6));
+    f(c->radius); f(c->radius_sq); f(c->user_cell_size); f(c->spec_radius); f(c->r_max); f(c->cell);
+    for (int64_t v : { (int64_t)c->opt_list_capacity, (int64_t)c->opt_query_limit, (int64_t)c->opt_sort_lists, (int64_t)c->opt_point_stride, (int64_t)c->opt_bucket_passes,
+                       (int64_t)c->opt_build, (int64_t)c->opt_query_kernel, (int64_t)c->brick_kmax, (int64_t)c->opt_speculate, (int64_t)c->opt_force_level,
+                       (int64_t)c->spec_n_sets, (int64_t)c->bgrid.nx, (int64_t)c->bgrid.ny, (int64_t)c->bgrid.nz })
+        k.push_back((uint64_t)v);
+    for (int d = 0; d < 3; d++) f(c->bgrid.bottom[d]);
+    f(c->bgrid.inv_cell);
+    for (auto& st : c->sets) {
+        k.push_back((uint64_t)(uintptr_t)st.u_pts_f32); k.push_back((uint64_t)(uintptr_t)st.u_pts_f64);
+        k.push_back((uint64_t)(uintptr_t)st.u_radii_f32); k.push_back((uint64_t)(uintptr_t)st.u_radii_f64);
+        k.push_back((uint64_t)st.n | ((uint64_t)st.is_f64 << 40) | ((uint64_t)st.has_radii << 41));
+    }
+    for (auto& row : c->active)
+        for (uint8_t a : row) k.push_back(a);
+    for (auto& ps : c->pairs) {
+        k.push_back((uint64_t)ps.capacity); k.push_back((uint64_t)ps.max_tasks); k.push_back((uint64_t)ps.in_host);
+    }
+    return k;
+}
+
+// ends a stream capture that an error path left open
+void abort_capture(tnsb_context* c)
+{
+    if (!c->capturing) return;
+    cudaGraph_t g = nullptr;
+    cudaStreamEndCapture(c->stream, &g);
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    c->capturing = false;
+}
+
 int run_impl(tnsb_context* c)
 {
     const auto t0 = std::chrono::steady_clock::now();
     int rc = validate(c);
     if (rc != TNSB_OK) return rc;
     DeviceGuard device_guard(c->device);
-    memset(&c->stats, 0, sizeof(c->stats));
+    struct CaptureGuard { tnsb_context* c; ~CaptureGuard() { abort_capture(c); } } capture_guard{ c };      // no exit path leaves the stream capturing
     const int n_sets = (int)c->sets.size();
     if (n_sets > 64) return fail(c, TNSB_ERR_LIMIT, "tnsb: at most 64 point sets are supported.");
-    c->pairs.resize((size_t)n_sets * n_sets);
-    for (auto& p : c->pairs) { p.valid = false; p.host_valid = false; p.n_ints = 0; p.n_neighbors = 0; p.n_lists = 0; }
     int64_t n_total = 0;
     for (auto& st : c->sets) n_total += st.n;
-    c->stats.n_points_total = n_total;
     cudaStream_t s = c->stream;
+    const size_t n_pairs = (size_t)n_sets * n_sets;
+
+    // ---- small problems in steady state: the enqueue phase of run() as ONE graph launch (the run is launch-latency bound: ~20 kernels
+    // and copies).  replay: the key of this run equals the key the graph was captured for.  capture: it equals the key of the previous
+    // run, which went through the speculative (no host round trip) path -- the same code below then runs under stream capture.
+    const bool small = c->opt_graph && n_total > 0 && n_total <= (1 << 18) && c->opt_query_kernel == 0 && c->pairs.size() == n_pairs;
+    std::vector<uint64_t> key;
+    if (small) key = make_run_key(c);
+    // (both need the PREVIOUS run to have had this very key: the replay leaves the host-side state of sets and pairs as that run left it)
+    const bool steady = small && !c->last_key.empty() && key == c->last_key;
+    const bool replay = steady && c->graph_exec && key == c->graph_key;
+    const bool capture = steady && !replay;
+    c->last_key.clear();
+    c->graph_run = replay || capture;
 
     GridParams gp;
     memset(&gp, 0, sizeof(gp));
-    if (n_total > 0) {
-        rc = build_grid(c, &gp, c->opt_query_kernel == 0, false);
-        if (rc != TNSB_OK) return rc;
-    } else {
-        for (int k = 0; k < EV_COUNT; k++) TNSB_CUDA(c, cudaEventRecord(c->ev[k], s));
-    }
-
-    // ---- queries, one launch per active ordered pair
-    std::vector<int> act;
-    for (int si = 0; si < n_sets; si++)
-        for (int sj = 0; sj < n_sets; sj++)
-            if (c->active[si][sj]) act.push_back(si * n_sets + sj);
-    const size_t n_pairs = (size_t)n_sets * n_sets;
-    TNSB_CUDA(c, c->d_counters.ensure(sizeof(PairCounters) * std::max<size_t>(n_pairs, 1)));
-    TNSB_CUDA(c, c->h_small.ensure(4096 + 2 * sizeof(PairCounters) * std::max<size_t>(n_pairs, 1)));
-    PairCounters* h_init = reinterpret_cast<PairCounters*>(c->h_small.as<char>() + 2048);
-    PairCounters* h_out = h_init + std::max<size_t>(n_pairs, 1);
+    PairCounters* h_init = nullptr;
+    PairCounters* h_out = nullptr;
     const int qlimit = c->opt_query_limit >= 0 ? (int)std::min<int64_t>(c->opt_query_limit, INT_MAX) : INT_MAX;
-
+    std::vector<int> act, todo;
     int brick_max_list = 0;
-    std::vector<int> todo;
-    for (int id : act) {
-        const int si = id / n_sets;
-        PairState& ps = c->pairs[id];
-        ps.n_lists = std::min(c->sets[si].n, qlimit);
-        ps.valid = true;
-        if (c->sets[si].n == 0 || n_total == 0) continue;
-        const int64_t want = (int64_t)ps.n_lists * (c->opt_list_capacity + 1) + 4096;
-        // zero-copy: the kernel's flushes go straight to mapped pinned host memory (no HBM copy of the lists, no D2H afterwards)
-        // zero-copy and sorted lists go together in the brick query (it sorts in shared memory); the cell kernel sorts in a post pass over HBM
-        const bool in_host = c->opt_host_results && c->opt_zero_copy && !(c->opt_sort_lists == 1 && !c->brick_mode);
-        if (in_host != ps.in_host) { ps.in_host = in_host; ps.capacity = 0; }
-        if (ps.in_host) {
-            TNSB_CUDA(c, ps.h_ragged.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(want, ps.capacity)));
-            ps.capacity = (int64_t)(ps.h_ragged.cap / sizeof(int32_t));
-        } else if (ps.capacity < want) {
-            TNSB_CUDA(c, ps.d_ragged.ensure(sizeof(int32_t) * (size_t)want));
-            ps.capacity = (int64_t)(ps.d_ragged.cap / sizeof(int32_t));
+
+    if (replay) {
+        c->stats = c->graph_stats;
+        for (auto& p : c->pairs) { p.host_valid = false; p.n_ints = 0; p.n_neighbors = 0; }
+        for (auto& hc : c->graph_host_copies) memcpy(hc.dst, hc.src, hc.bytes);
+        act = c->graph_act;
+        for (int id : act)
+            if (c->pairs[id].n_lists > 0) todo.push_back(id);
+        h_init = reinterpret_cast<PairCounters*>(c->h_small.as<char>() + 2048);
+        h_out = h_init + std::max<size_t>(n_pairs, 1);
+        c->spec_used = true;
+        *(c->h_small.as<int>() + 32) = 0;
+        TNSB_CUDA(c, cudaEventRecord(c->ev[EV_BEGIN], s));
+        TNSB_CUDA(c, cudaGraphLaunch(c->graph_exec, s));
+    } else {
+        memset(&c->stats, 0, sizeof(c->stats));
+        c->pairs.resize(n_pairs);
+        for (auto& p : c->pairs) { p.valid = false; p.host_valid = false; p.n_ints = 0; p.n_neighbors = 0; p.n_lists = 0; }
+        c->stats.n_points_total = n_total;
+        c->cur_host_copies.clear();
+        if (capture) {
+            TNSB_CUDA(c, cudaEventRecord(c->ev[EV_BEGIN], s));
+            if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) c->capturing = true;
+            else { cudaGetLastError(); c->graph_run = false; }
         }
-        TNSB_CUDA(c, ps.d_list_pos.ensure(sizeof(long long) * (size_t)c->sets[si].n, 1.1));
-        todo.push_back(id);
+        if (n_total > 0) {
+            rc = build_grid(c, &gp, c->opt_query_kernel == 0, false);
+            if (rc != TNSB_OK) {
+                if (c->capturing) { abort_capture(c); c->opt_graph = 0; return run_impl(c); }      // not capturable after all: plain runs from now on
+                return rc;
+            }
+        } else {
+            for (int k = 0; k < EV_COUNT; k++) TNSB_EVENT(c, cudaEventRecord(c->ev[k], s));
+        }
+
+        // ---- queries, one launch per active ordered pair
+        for (int si = 0; si < n_sets; si++)
+            for (int sj = 0; sj < n_sets; sj++)
+                if (c->active[si][sj]) act.push_back(si * n_sets + sj);
+        TNSB_CUDA(c, c->d_counters.ensure(sizeof(PairCounters) * std::max<size_t>(n_pairs, 1)));
+        TNSB_CUDA(c, c->h_small.ensure(4096 + 2 * sizeof(PairCounters) * std::max<size_t>(n_pairs, 1)));
+        h_init = reinterpret_cast<PairCounters*>(c->h_small.as<char>() + 2048);
+        h_out = h_init + std::max<size_t>(n_pairs, 1);
+
+        for (int id : act) {
+            const int si = id / n_sets;
+            PairState& ps = c->pairs[id];
+            ps.n_lists = std::min(c->sets[si].n, qlimit);
+            ps.valid = true;
+            if (c->sets[si].n == 0 || n_total == 0) continue;
+            const int64_t want = (int64_t)ps.n_lists * (c->opt_list_capacity + 1) + 4096;
+            // zero-copy: the kernel's flushes go straight to mapped pinned host memory (no HBM copy of the lists, no D2H afterwards)
+            // zero-copy and sorted lists go together in the brick query (it sorts in shared memory); the cell kernel sorts in a post pass over HBM
+            const bool in_host = c->opt_host_results && c->opt_zero_copy && !(c->opt_sort_lists == 1 && !c->brick_mode);
+            if (in_host != ps.in_host) { ps.in_host = in_host; ps.capacity = 0; }
+            if (ps.in_host) {
+                TNSB_CUDA(c, ps.h_ragged.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(want, ps.capacity)));
+                ps.capacity = (int64_t)(ps.h_ragged.cap / sizeof(int32_t));
+            } else if (ps.capacity < want) {
+                TNSB_CUDA(c, ps.d_ragged.ensure(sizeof(int32_t) * (size_t)want));
+                ps.capacity = (int64_t)(ps.d_ragged.cap / sizeof(int32_t));
+            }
+            TNSB_CUDA(c, ps.d_list_pos.ensure(sizeof(long long) * (size_t)c->sets[si].n, 1.1));
+            todo.push_back(id);
+        }
     }
     int attempts = 0;
+    bool enqueued = replay;         // the graph launch already enqueued the first round of queries
     while (!todo.empty()) {
         if (++attempts > 4) return fail(c, TNSB_ERR_LIMIT, "tnsb: neighbour list buffer kept overflowing.");
-        for (int id : todo) {
-            PairCounters z;
-            memset(&z, 0, sizeof(z));
-            h_init[id] = z;
-        }
-        for (int id : todo)
-            TNSB_CUDA(c, cudaMemcpyAsync(c->d_counters.as<PairCounters>() + id, h_init + id, sizeof(PairCounters), cudaMemcpyHostToDevice, s));
-        for (int id : todo) {
-            const int si = id / n_sets, sj = id % n_sets;
-            if (c->brick_mode) rc = query_pair_brick(c, si, sj, c->d_counters.as<PairCounters>() + id);
-            else rc = c->key64 ? query_pair<uint64_t>(c, si, sj, gp, c->d_counters.as<PairCounters>() + id)
-                               : query_pair<uint32_t>(c, si, sj, gp, c->d_counters.as<PairCounters>() + id);
-            if (rc != TNSB_OK) return rc;
-        }
-        TNSB_CUDA(c, cudaMemcpyAsync(h_out, c->d_counters.p, sizeof(PairCounters) * n_pairs, cudaMemcpyDeviceToHost, s));
         int* const h_spec_flag = c->h_small.as<int>() + 32;
-        *h_spec_flag = 0;
-        if (c->spec_used) TNSB_CUDA(c, cudaMemcpyAsync(h_spec_flag, c->d_reduce.as<int>() + 8, sizeof(int), cudaMemcpyDeviceToHost, s));
+        if (!enqueued) {
+            for (int id : todo) {
+                PairCounters z;
+                memset(&z, 0, sizeof(z));
+                h_init[id] = z;
+            }
+            rc = TNSB_OK;
+            for (int id : todo)
+                if (cudaMemcpyAsync(c->d_counters.as<PairCounters>() + id, h_init + id, sizeof(PairCounters), cudaMemcpyHostToDevice, s) != cudaSuccess) rc = TNSB_ERR_CUDA;
+            for (int id : todo) {
+                if (rc != TNSB_OK) break;
+                const int si = id / n_sets, sj = id % n_sets;
+                if (c->brick_mode) rc = query_pair_brick(c, si, sj, c->d_counters.as<PairCounters>() + id);
+                else rc = c->key64 ? query_pair<uint64_t>(c, si, sj, gp, c->d_counters.as<PairCounters>() + id)
+                                   : query_pair<uint32_t>(c, si, sj, gp, c->d_counters.as<PairCounters>() + id);
+            }
+            *h_spec_flag = 0;
+            if (rc == TNSB_OK && cudaMemcpyAsync(h_out, c->d_counters.p, sizeof(PairCounters) * n_pairs, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = TNSB_ERR_CUDA;
+            if (rc == TNSB_OK && c->spec_used && cudaMemcpyAsync(h_spec_flag, c->d_reduce.as<int>() + 8, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = TNSB_ERR_CUDA;
+            if (c->capturing) {
+                // end of the captured region: instantiate (or give up on graphs for this context) and launch what was just recorded
+                cudaGraph_t g = nullptr;
+                cudaError_t e = cudaStreamEndCapture(s, &g);
+                c->capturing = false;
+                if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+                if (rc == TNSB_OK && e == cudaSuccess && g && c->spec_used) e = cudaGraphInstantiate(&c->graph_exec, g, 0);
+                else if (e == cudaSuccess) e = cudaErrorUnknown;
+                if (g) cudaGraphDestroy(g);
+                if (e != cudaSuccess || !c->graph_exec) {
+                    cudaGetLastError();
+                    c->graph_exec = nullptr;
+                    c->opt_graph = 0;
+                    return run_impl(c);
+                }
+                c->graph_key = key;
+                c->graph_act = act;
+                c->graph_stats = c->stats;
+                c->graph_host_copies = c->cur_host_copies;
+                TNSB_CUDA(c, cudaGraphLaunch(c->graph_exec, s));
+            } else if (rc != TNSB_OK) {
+                cudaGetLastError();
+                return rc == TNSB_ERR_CUDA ? fail(c, TNSB_ERR_CUDA, "CUDA error while enqueuing the queries.") : rc;
+            }
+        }
+        enqueued = false;
         TNSB_CUDA(c, cudaStreamSynchronize(s));
         if (c->spec_used && *h_spec_flag) {
             // the cloud left the grid that was reused speculatively (or the radius range changed): this run's lists are void.
@@ -973,6 +1119,14 @@ int run_impl(tnsb_context* c)
         }
         todo.swap(again);
     }
+    if (c->capturing) {
+        // nothing to search (no active pair, empty searching sets): the capture holds only the build -- drop it
+        abort_capture(c);
+        c->graph_run = false;
+        return run_impl(c);
+    }
+    // the next run may be captured if it looks exactly like this one did and this one took the path without a host round trip
+    if (small && c->spec_used && c->stats.n_reruns == 0) c->last_key = key;
     // hit column height of the next run: the short columns (more warps per SM) while the longest list leaves some headroom
     if (c->brick_mode && !act.empty()) c->brick_kmax = brick_max_list <= 62 ? 64 : (brick_max_list <= 92 ? 96 : 128);
     c->stats.max_list = brick_max_list;
@@ -986,7 +1140,7 @@ int run_impl(tnsb_context* c)
         }
         TNSB_CUDA(c, cudaGetLastError());
     }
-    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_QUERY], s));
+    TNSB_EVENT(c, cudaEventRecord(c->ev[EV_QUERY], s));
 
     // ---- host mirror of the lists
     for (int id : act) {
@@ -1005,9 +1159,17 @@ int run_impl(tnsb_context* c)
         c->stats.d2h_bytes += (int64_t)sizeof(int32_t) * ps.n_ints + (int64_t)sizeof(long long) * ps.n_lists;
         ps.host_valid = true;
     }
-    TNSB_CUDA(c, cudaEventRecord(c->ev[EV_DOWNLOAD], s));
+    TNSB_EVENT(c, cudaEventRecord(c->ev[EV_DOWNLOAD], s));
     TNSB_CUDA(c, cudaStreamSynchronize(s));
 
+    if (c->graph_run) {
+        // the enqueue phase was one graph launch: only the total is timed
+        c->stats.ms_total_device = ev_ms(c, EV_BEGIN, EV_QUERY);
+        c->stats.ms_download = ev_ms(c, EV_QUERY, EV_DOWNLOAD);
+        c->stats.graph_replay = 1;
+        c->stats.ms_wall = ms_since(t0);
+        return TNSB_OK;
+    }
     c->stats.ms_upload = ev_ms(c, EV_BEGIN, EV_UPLOAD);
     c->stats.ms_aabb = ev_ms(c, EV_UPLOAD, EV_AABB);
     c->stats.ms_keys = ev_ms(c, EV_AABB, EV_KEYS);
@@ -1082,6 +1244,7 @@ int tnsb_create(tnsb_context** out, int device)
     if (const char* bk = getenv("TNSB_BUILD")) c->opt_build = (bk[0] == '1') ? 1 : 0;
     if (const char* bp = getenv("TNSB_BUCKET_PASSES")) c->opt_bucket_passes = atoi(bp);
     if (const char* sp = getenv("TNSB_SPECULATE")) c->opt_speculate = atoi(sp) != 0;
+    if (const char* gr = getenv("TNSB_GRAPH")) c->opt_graph = atoi(gr) != 0;
     if (const char* lv = getenv("TNSB_BRICK_LEVEL")) c->opt_force_level = atoi(lv);
     for (int k = 0; k < EV_COUNT; k++) cudaEventCreate(&c->ev[k]);
     *out = c;
@@ -1094,7 +1257,9 @@ void tnsb_destroy(tnsb_context* c)
     DeviceGuard device_guard(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->registered) cudaHostUnregister(const_cast<void*>(kv.first));
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     for (auto& st : c->sets) {
+        st.hs_pts.release(); st.hs_radii.release();
         st.up_pts.release(); st.up_radii.release(); st.cv_pts.release(); st.cv_radii.release();
         for (int b = 0; b < 2; b++) { st.keys[b].release(); st.vals[b].release(); }
         st.sorted.release(); st.sorted_r2.release(); st.cell_key.release(); st.cell_start.release(); st.tile_heads.release();
