@@ -430,9 +430,26 @@ def bench_c4_twoset(t, torch, timer, stream, with_cpu):
 def bench_small_n(t, torch, stream, with_cpu):
     """The reference's own micro-benchmark (tests/tests.cpp:239-279): 9 261 lattice points, z-sorted, 1000 x run(), wall clock per call."""
     from treensearch_b200 import clouds
-    pts, r = clouds.sph_lattice(9261)
+    pts, r = clouds.sph_lattice(9000)              # benchmark_one_dynamic_set(9000): a 21^3 = 9261 point lattice
     pts = pts.copy()
     out = {"config": f"{pts.shape[0]} lattice points (tests/tests.cpp:239-279), z-sorted, 1000 run() calls, host wall clock per call"}
+    # the reference's OWN test program, unmodified, once linked to this engine through the drop-in header and once built with the
+    # reference's own library: the "Runtime parallel SIMD" line both print after 1000 x run() (oracle/Makefile: ref-tests)
+    from oracle import loader as _ld
+    import re
+    import subprocess
+    for key, exe in (("cpp_program_on_b200_ms_per_run", _ld.REF_TESTS_BIN), ("cpp_program_reference_ms_per_run", getattr(_ld, "REF_TESTS_NATIVE_BIN", ""))):
+        if not (with_cpu and exe and os.path.exists(exe)):
+            continue
+        env = dict(os.environ)
+        env["OMP_NUM_THREADS"] = str(_reference_threads())
+        try:
+            res = subprocess.run([exe], capture_output=True, text=True, timeout=600, env=env)
+            m = re.search(r"Runtime parallel SIMD: ([0-9.eE+-]+) ms", res.stdout)
+            if m:
+                out[key] = float(m.group(1))
+        except Exception as e:      # noqa: BLE001 -- a missing / failing helper binary must not take the bench line down
+            out[key + "_error"] = str(e)[:200]
     for name, host in (("host_arrays_ms_per_run", True), ("device_resident_ms_per_run", False)):
         arr = pts.copy() if host else torch.from_numpy(pts).cuda()
         eng = t.TreeNSearch(0)
@@ -452,6 +469,7 @@ def bench_small_n(t, torch, stream, with_cpu):
             eng.run()
         torch.cuda.synchronize()
         out[name] = (time.perf_counter() - t0)
+        out[name.replace("_ms_per_run", "_graph_replay")] = int(eng.stats()["graph_replay"])
         eng.close()
     if with_cpu:
         cores = _reference_threads()

@@ -136,6 +136,7 @@ struct PairState {
     int n_lists = 0;
     bool valid = false;
     bool host_valid = false;
+    bool pos_copied = false;   // list_pos is already on its way to the host (enqueued right behind the query, before the counters are known)
 };
 
 enum Stage { EV_BEGIN = 0, EV_UPLOAD, EV_AABB, EV_KEYS, EV_SORT, EV_REORDER, EV_CELLS, EV_QUERY, EV_DOWNLOAD, EV_COUNT };
@@ -193,6 +194,7 @@ struct tnsb_context {
     struct HostCopy { void* dst; const void* src; size_t bytes; };
     std::vector<HostCopy> graph_host_copies, cur_host_copies;
     bool capturing = false;        // stream capture in progress: no event records, no synchronisation
+    cudaStream_t cap_user_stream = nullptr;   // while capturing, `stream` is the engine's own stream (the legacy default stream cannot capture); this is the caller's
     bool graph_run = false;        // this run went through the graph: per-stage timings are not available
     int opt_force_level = -1;
     bool brick_mode = false;       // grid built last: half-radius cells + linear row keys (brick query) or cell = r + 3-D Morton keys (cell kernel, zsort)
@@ -926,6 +928,7 @@ void abort_capture(tnsb_context* c)
     if (g) cudaGraphDestroy(g);
     cudaGetLastError();
     c->capturing = false;
+    c->stream = c->cap_user_stream;
 }
 
 int run_impl(tnsb_context* c)
@@ -939,7 +942,7 @@ int run_impl(tnsb_context* c)
     if (n_sets > 64) return fail(c, TNSB_ERR_LIMIT, "tnsb: at most 64 point sets are supported.");
     int64_t n_total = 0;
     for (auto& st : c->sets) n_total += st.n;
-    cudaStream_t s = c->stream;
+    cudaStream_t s = c->stream;            // (the engine's own stream while the run is being captured)
     const size_t n_pairs = (size_t)n_sets * n_sets;
 
     // ---- small problems in steady state: the enqueue phase of run() as ONE graph launch (the run is launch-latency bound: ~20 kernels
@@ -965,7 +968,7 @@ int run_impl(tnsb_context* c)
 
     if (replay) {
         c->stats = c->graph_stats;
-        for (auto& p : c->pairs) { p.host_valid = false; p.n_ints = 0; p.n_neighbors = 0; }
+        for (auto& p : c->pairs) { p.host_valid = false; p.n_ints = 0; p.n_neighbors = 0; }      // (pos_copied stays as the captured run left it)
         for (auto& hc : c->graph_host_copies) memcpy(hc.dst, hc.src, hc.bytes);
         act = c->graph_act;
         for (int id : act)
@@ -979,13 +982,24 @@ int run_impl(tnsb_context* c)
     } else {
         memset(&c->stats, 0, sizeof(c->stats));
         c->pairs.resize(n_pairs);
-        for (auto& p : c->pairs) { p.valid = false; p.host_valid = false; p.n_ints = 0; p.n_neighbors = 0; p.n_lists = 0; }
+        for (auto& p : c->pairs) { p.valid = false; p.host_valid = false; p.pos_copied = false; p.n_ints = 0; p.n_neighbors = 0; p.n_lists = 0; }
         c->stats.n_points_total = n_total;
         c->cur_host_copies.clear();
-        if (capture) {
+        if (capture && c->own_stream) {
+            // recorded on the engine's own stream (any stream will do for a capture; the caller's may be the legacy default stream,
+            // which cannot capture), launched on the caller's
             TNSB_CUDA(c, cudaEventRecord(c->ev[EV_BEGIN], s));
-            if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) c->capturing = true;
-            else { cudaGetLastError(); c->graph_run = false; }
+            if (cudaStreamBeginCapture(c->own_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                c->capturing = true;
+                c->cap_user_stream = c->stream;
+                c->stream = c->own_stream;
+                s = c->stream;
+            } else {
+                cudaGetLastError();
+                c->graph_run = false;
+            }
+        } else if (capture) {
+            c->graph_run = false;
         }
         if (n_total > 0) {
             rc = build_grid(c, &gp, c->opt_query_kernel == 0, false);
@@ -1052,11 +1066,23 @@ int run_impl(tnsb_context* c)
             *h_spec_flag = 0;
             if (rc == TNSB_OK && cudaMemcpyAsync(h_out, c->d_counters.p, sizeof(PairCounters) * n_pairs, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = TNSB_ERR_CUDA;
             if (rc == TNSB_OK && c->spec_used && cudaMemcpyAsync(h_spec_flag, c->d_reduce.as<int>() + 8, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = TNSB_ERR_CUDA;
+            // list_pos has a size that does not depend on the outcome: its copy to the host rides behind the query (no second round trip)
+            if (c->opt_host_results) {
+                for (int id : todo) {
+                    PairState& ps = c->pairs[id];
+                    if (rc != TNSB_OK || ps.n_lists == 0) continue;
+                    if (ps.h_list_pos.ensure(sizeof(long long) * (size_t)c->sets[id / n_sets].n, 1.25) != cudaSuccess ||
+                        cudaMemcpyAsync(ps.h_list_pos.p, ps.d_list_pos.p, sizeof(long long) * (size_t)ps.n_lists, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = TNSB_ERR_CUDA;
+                    ps.pos_copied = true;
+                }
+            }
             if (c->capturing) {
                 // end of the captured region: instantiate (or give up on graphs for this context) and launch what was just recorded
                 cudaGraph_t g = nullptr;
                 cudaError_t e = cudaStreamEndCapture(s, &g);
                 c->capturing = false;
+                c->stream = c->cap_user_stream;
+                s = c->stream;
                 if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
                 if (rc == TNSB_OK && e == cudaSuccess && g && c->spec_used) e = cudaGraphInstantiate(&c->graph_exec, g, 0);
                 else if (e == cudaSuccess) e = cudaErrorUnknown;
@@ -1155,7 +1181,7 @@ int run_impl(tnsb_context* c)
             TNSB_CUDA(c, ps.h_ragged.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(ps.n_ints, 1), 1.25));
             TNSB_CUDA(c, cudaMemcpyAsync(ps.h_ragged.p, ps.d_ragged.p, sizeof(int32_t) * (size_t)ps.n_ints, cudaMemcpyDeviceToHost, s));
         }
-        TNSB_CUDA(c, cudaMemcpyAsync(ps.h_list_pos.p, ps.d_list_pos.p, sizeof(long long) * (size_t)ps.n_lists, cudaMemcpyDeviceToHost, s));
+        if (!ps.pos_copied) TNSB_CUDA(c, cudaMemcpyAsync(ps.h_list_pos.p, ps.d_list_pos.p, sizeof(long long) * (size_t)ps.n_lists, cudaMemcpyDeviceToHost, s));
         c->stats.d2h_bytes += (int64_t)sizeof(int32_t) * ps.n_ints + (int64_t)sizeof(long long) * ps.n_lists;
         ps.host_valid = true;
     }
