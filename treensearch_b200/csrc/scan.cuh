@@ -65,30 +65,59 @@ __global__ void __launch_bounds__(kScanThreads) scan_partials_kernel(uint32_t* _
     if (threadIdx.x == 0 && total_out) *total_out = running;
 }
 
+// out2 (optional): a second copy of the result limited to its first n2 entries (the bucket build's scatter cursors = the prefix table
+// without its last entry), written here instead of by a separate device-to-device copy.  A thread owns kScanItems = 8 consecutive values:
+// two 128-bit loads / stores when the arrays are 16-byte aligned (a scalar 4-byte store per value makes eight partial writes per sector).
 __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
-                                                                  const uint32_t* __restrict__ tile_sums, int64_t n)
+                                                                  const uint32_t* __restrict__ tile_sums, int64_t n, uint32_t* __restrict__ out2, int64_t n2, int vec_ok)
 {
     __shared__ uint32_t warp_sums[8];
     // blocked arrangement: thread t owns kScanItems consecutive values
     const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
     uint32_t v[kScanItems];
+    const bool full = vec_ok && base + kScanItems <= n;
+    if (full) {
+        const uint4 a = reinterpret_cast<const uint4*>(in + base)[0], b = reinterpret_cast<const uint4*>(in + base)[1];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < kScanItems; i++) v[i] = (base + i < n) ? in[base + i] : 0u;
+    }
     uint32_t s = 0;
 #pragma unroll
-    for (int i = 0; i < kScanItems; i++) {
-        v[i] = (base + i < n) ? in[base + i] : 0u;
-        s += v[i];
-    }
+    for (int i = 0; i < kScanItems; i++) s += v[i];
     uint32_t total;
     uint32_t ex = block_exclusive_scan_256(s, warp_sums, total) + tile_sums[blockIdx.x];
+    uint32_t r[kScanItems];
 #pragma unroll
     for (int i = 0; i < kScanItems; i++) {
-        if (base + i < n) out[base + i] = ex;
+        r[i] = ex;
         ex += v[i];
+    }
+    if (full) {
+        const uint4 a = make_uint4(r[0], r[1], r[2], r[3]), b = make_uint4(r[4], r[5], r[6], r[7]);
+        reinterpret_cast<uint4*>(out + base)[0] = a;
+        reinterpret_cast<uint4*>(out + base)[1] = b;
+        if (out2 && base + kScanItems <= n2) {
+            reinterpret_cast<uint4*>(out2 + base)[0] = a;
+            reinterpret_cast<uint4*>(out2 + base)[1] = b;
+        } else if (out2) {
+#pragma unroll
+            for (int i = 0; i < kScanItems; i++)
+                if (base + i < n2) out2[base + i] = r[i];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kScanItems; i++) {
+            if (base + i < n) out[base + i] = r[i];
+            if (out2 && base + i < n2) out2[base + i] = r[i];
+        }
     }
 }
 
 // temp must hold ceil(n / kScanTile) uint32.  In-place (out == in) is allowed.  total_out (device pointer) may be null.
-inline int exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uint32_t* temp, uint32_t* total_out, cudaStream_t stream)
+inline int exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uint32_t* temp, uint32_t* total_out, cudaStream_t stream, uint32_t* out2 = nullptr,
+                              int64_t n2 = 0)
 {
     if (n <= 0) {
         if (total_out) cudaMemsetAsync(total_out, 0, sizeof(uint32_t), stream);
@@ -97,7 +126,8 @@ inline int exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uint
     const int n_tiles = (int)ceil_div64(n, kScanTile);
     scan_tile_sums_kernel<<<n_tiles, kScanThreads, 0, stream>>>(in, temp, n);
     scan_partials_kernel<<<1, kScanThreads, 0, stream>>>(temp, n_tiles, total_out);
-    scan_apply_kernel<<<n_tiles, kScanThreads, 0, stream>>>(in, out, temp, n);
+    const int vec_ok = (((uintptr_t)in | (uintptr_t)out | (uintptr_t)out2) & 15u) == 0 ? 1 : 0;
+    scan_apply_kernel<<<n_tiles, kScanThreads, 0, stream>>>(in, out, temp, n, out2, n2, vec_ok);
     return 3;
 }
 

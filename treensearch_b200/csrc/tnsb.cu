@@ -367,8 +367,7 @@ int build_sets(tnsb_context* c, const GridParams& gp, bool need_order, const int
         if (st.bucket) {
             const int64_t n_entries = n_keys + 1;
             uint32_t* first = st.first.as<uint32_t>();
-            launches += exclusive_scan_u32(first, first, n_entries, first + n_entries, nullptr, s);
-            TNSB_CUDA(c, cudaMemcpyAsync(st.cursor.p, first, sizeof(uint32_t) * (size_t)n_keys, cudaMemcpyDeviceToDevice, s));
+            launches += exclusive_scan_u32(first, first, n_entries, first + n_entries, nullptr, s, st.cursor.as<uint32_t>(), n_keys);     // + the scatter cursors
             c->stats.sort_passes = std::max(c->stats.sort_passes, 1);
         } else {
             TNSB_CUDA(c, c->sort_temp.ensure(sizeof(uint32_t) * (size_t)radix_sort_temp_elems<Key>(st.n), 1.1));
@@ -568,8 +567,7 @@ int build_sets_brick(tnsb_context* c, const BrickGrid& bg)
     for (auto& st : c->sets) {
         if (st.n == 0) continue;
         uint32_t* first = st.first.as<uint32_t>();
-        launches += exclusive_scan_u32(first, first, n_entries, first + n_entries, nullptr, s);
-        TNSB_CUDA(c, cudaMemcpyAsync(st.cursor.p, first, sizeof(uint32_t) * (size_t)n_keys, cudaMemcpyDeviceToDevice, s));
+        launches += exclusive_scan_u32(first, first, n_entries, first + n_entries, nullptr, s, st.cursor.as<uint32_t>(), n_keys);     // + the scatter cursors
         c->stats.sort_passes = std::max(c->stats.sort_passes, 1);
     }
     TNSB_EVENT(c, cudaEventRecord(c->ev[EV_SORT], s));
