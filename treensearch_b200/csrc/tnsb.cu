@@ -390,7 +390,7 @@ int build_sets(tnsb_context* c, const GridParams& gp, bool need_order, const int
             int passes = c->opt_bucket_passes > 0 ? c->opt_bucket_passes : (int)std::min<int64_t>(16, std::max<int64_t>(1, ((int64_t)st.n * 16 + (56ll << 20) - 1) / (56ll << 20)));
             for (int p = 0; p < passes; p++) {
                 const Key lo = (Key)(n_keys * p / passes), hi = (Key)(n_keys * (p + 1) / passes);
-                bucket_scatter_kernel<Key><<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.d_stride, st.has_radii ? st.d_radii : nullptr, st.keys[0].as<Key>(), st.n,
+                bucket_scatter_kernel<Key><<<ceil_div(st.n, 256 * kScatterItems), 256, 0, s>>>(st.d_pts, st.d_stride, st.has_radii ? st.d_radii : nullptr, st.keys[0].as<Key>(), st.n,
                                                                               st.cursor.as<uint32_t>(), st.sorted.as<float4>(), st.sorted_r2.as<float>(), lo, hi);
             }
             launches += passes - 1;
@@ -578,7 +578,7 @@ int build_sets_brick(tnsb_context* c, const BrickGrid& bg)
         const int passes = c->opt_bucket_passes > 0 ? c->opt_bucket_passes : (int)std::min<int64_t>(16, std::max<int64_t>(1, ((int64_t)st.n * 16 + (56ll << 20) - 1) / (56ll << 20)));
         for (int p = 0; p < passes; p++) {
             const uint32_t lo = (uint32_t)(n_keys * p / passes), hi = (uint32_t)(n_keys * (p + 1) / passes);
-            bucket_scatter_kernel<uint32_t><<<ceil_div(st.n, 256), 256, 0, s>>>(st.d_pts, st.d_stride, st.has_radii ? st.d_radii : nullptr, st.keys[0].as<uint32_t>(), st.n,
+            bucket_scatter_kernel<uint32_t><<<ceil_div(st.n, 256 * kScatterItems), 256, 0, s>>>(st.d_pts, st.d_stride, st.has_radii ? st.d_radii : nullptr, st.keys[0].as<uint32_t>(), st.n,
                                                                               st.cursor.as<uint32_t>(), st.sorted.as<float4>(), st.sorted_r2.as<float>(), lo, hi);
         }
         launches += passes;
