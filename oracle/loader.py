@@ -35,6 +35,7 @@ def build(quiet: bool = True) -> None:
 
 
 REF_TESTS_BIN = os.path.join(_HERE, "_ref", "ref_tests_on_b200")
+REF_STRESS_BIN = os.path.join(_HERE, "_ref", "ref_stress_on_b200")                # the reference's dynamic_emitter_stress_test on the CUDA engine
 REF_TESTS_NATIVE_BIN = os.path.join(_HERE, "_ref", "ref_tests_native")      # the same program built with the reference's own library
 
 
