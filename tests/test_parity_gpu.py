@@ -116,6 +116,46 @@ def test_resize_variable_radius(tnsb):                # tests/tests.cpp:188-237
         assert_matches_port(eng, sub)
 
 
+def test_combinatorial_counts_with_zsort(tnsb):
+    """combinatorial_stress_test of the reference (tests/tests.cpp:287-427): every combination of "interesting" particle counts over
+    1, 2 and 3 variable-radius sets (coordinates in [0, 10), radii in [0.5, 1.0], all searches active), run, prepare_zsort +
+    apply_zsort of positions and radii, run again.  The reference only looks for crashes there (its comparison is compiled out);
+    here both runs of every case are compared with the brute-force port.  The count lists are thinned for 2 and 3 sets (the full
+    cross product is 175 000 engine constructions)."""
+    rs = np.random.RandomState(42)
+    counts1 = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 15, 16, 17, 23, 24, 25, 100, 1000, 10000, 10001, 10009]
+    counts2 = [0, 1, 2, 8, 9, 17, 100, 1000, 10007]
+    counts3 = [0, 1, 17, 1000]
+    combos = [(a,) for a in counts1] + [(a, b) for a in counts2 for b in counts2] + [(a, b, c) for a in counts3 for b in counts3 for c in counts3]
+    for counts in combos:
+        sets = []
+        for n in counts:
+            p = (rs.random_sample((n, 3)) * 10.0).astype(np.float32)
+            r = (0.5 + 0.5 * rs.random_sample(n)).astype(np.float32)
+            sets.append((p, r))
+        k = len(counts)
+        pairs = [(i, j) for i in range(k) for j in range(k)]
+        case = dict(sets=sets, radius=None, pairs=pairs, symmetric=True)
+        eng = tnsb.TreeNSearch()
+        for (p, r) in sets:
+            eng.add_point_set(p, r, variable_radius=True)
+        eng.set_all_searches(True)
+        eng.run()
+        check = sum(counts) <= 12000 or len(counts) == 1          # the brute-force port is quadratic: the largest pairs are run, not compared
+        if check:
+            assert_matches_port(eng, case)
+        eng.prepare_zsort()
+        for s, (p, r) in enumerate(sets):
+            if counts[s] > 0:
+                eng.apply_zsort(s, p, 3)
+                eng.apply_zsort(s, r, 1)
+        eng.run()
+        if check:
+            assert_matches_port(eng, case)
+        assert eng.stats()["n_queries"] == sum(counts) * k
+        eng.close()
+
+
 def test_dynamic_emitter_style_sequence(tnsb):       # tests/tests.cpp:434-514 (shortened): add / remove / replace with empty sets
     rs = np.random.RandomState(123)
     eng = tnsb.TreeNSearch()
