@@ -6,7 +6,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 # 4th launch of the query kernel: the steady-state variant (the first run uses the tall hit columns)
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:brick_query -s 3 -c 1 -f -o gpurun_out/r2_brick_query \
     python tools/run_workload.py --steps 5 > gpurun_out/r2_ncu_brick_query.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:brick_scatter\|bucket_scatter -s 3 -c 1 -f -o gpurun_out/r2_scatter \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:bucket_scatter -s 9 -c 1 -f -o gpurun_out/r2_scatter \
     python tools/run_workload.py --steps 5 > gpurun_out/r2_ncu_scatter.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:brick_query -s 3 -c 1 -f -o gpurun_out/r2_brick_query_dambreak \
     python tools/run_workload.py --steps 5 --workload dambreak > gpurun_out/r2_ncu_brick_query_dambreak.log 2>&1

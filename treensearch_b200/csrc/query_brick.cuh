@@ -151,7 +151,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "{\n"
         ".reg .pred p;\n"
         "BRICK_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"      // suspend-time hint: the thread sleeps until the phase completes instead of spinning through issue slots
         "@p bra BRICK_DONE;\n"
         "bra BRICK_WAIT;\n"
         "BRICK_DONE:\n"
