@@ -42,4 +42,33 @@ for kernel in (0, 1):
     eng.set_active_search(0, 0, True)
     eng.run()
     total += eng.stats()["n_neighbors"]
+# steady state: speculative grid reuse, graph capture + replay, host results (zero-copy, ascending lists)
+case = cases.GOLDEN_CASES["uniform_fixed_5000"]()
+pts5 = case["sets"][0][0].copy()
+eng = t.TreeNSearch()
+eng.set_search_radius(case["radius"])
+eng.add_point_set(pts5)
+eng.set_active_search(0, 0, True)
+for _ in range(6):
+    pts5 += np.float32(1e-4)
+    eng.run()
+total += eng.stats()["n_neighbors"] + eng.stats()["graph_replay"]
+# heavy bricks with few queries (single-query warp tasks) and the latency-optimised global slow path: a sparse searching set next to a
+# dense searched slab, variable radii, symmetric and not
+rs = np.random.RandomState(5)
+p0 = rs.random_sample((3000, 3)).astype(np.float32)
+p1 = rs.random_sample((60000, 3)).astype(np.float32)
+p1[:, 2] *= np.float32(0.02)
+r0 = (0.05 * (1.0 + 0.5 * rs.random_sample(3000))).astype(np.float32)
+r1 = (0.05 * (0.8 + 0.4 * rs.random_sample(60000))).astype(np.float32)
+for sym in (True, False):
+    eng = t.TreeNSearch()
+    eng.add_point_set(p0, r0, variable_radius=True)
+    eng.add_point_set(p1, r1, variable_radius=True)
+    for (i, j) in ((0, 0), (0, 1), (1, 0)):
+        eng.set_active_search(i, j, True)
+    eng.set_symmetric_search(sym)
+    eng.run()
+    eng.run()
+    total += eng.stats()["n_neighbors"] + eng.stats()["n_slow_queries"]
 print("sanitize_small done, neighbours:", total)
