@@ -353,7 +353,7 @@ def bench_c3_dambreak(t, torch, timer, stream, n, with_cpu):
         eng.prepare_zsort()
         eng.apply_zsort(0, d_pts, 3)
 
-    eng.run(); eng.run()                              # warm-up (buffers, column height)
+    eng.run(); zsort(); eng.run()                     # warm-up (buffers of run() and of the zsort path, column height)
     ms_run, ms_zs = [], []
     for step in range(20):
         if step % 10 == 0:
