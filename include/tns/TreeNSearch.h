@@ -60,7 +60,7 @@ namespace tns
 		inline NeighborList get_neighborlist(const int set_i, const int set_j, const int point_i) const
 		{
 			const PairView& v = views_[(size_t)set_i * (size_t)n_sets_ + (size_t)set_j];
-			return NeighborList(v.ragged + v.list_pos[point_i]);
+			return NeighborList(v.list_pos32 ? v.ragged + v.list_pos32[point_i] : v.ragged + v.list_pos[point_i]);
 		}
 
 		template<typename FUNC>
@@ -173,7 +173,7 @@ namespace tns
 		tnsb_context* native_handle() const { return ctx_; }
 
 	private:
-		struct PairView { const int* ragged = nullptr; const int64_t* list_pos = nullptr; };
+		struct PairView { const int* ragged = nullptr; const int64_t* list_pos = nullptr; const uint32_t* list_pos32 = nullptr; };
 
 		[[noreturn]] static void fail(const char* msg) { std::cout << msg << std::endl; exit(-1); }
 		void ok(const int rc) const { if (rc < 0) { fail(tnsb_last_error(ctx_)); } }
@@ -196,7 +196,11 @@ namespace tns
 				for (int j = 0; j < n_sets_; j++) {
 					if (!this->is_search_active(i, j)) { continue; }
 					PairView v; int64_t n_ints = 0;
-					ok(tnsb_get_neighborlists(ctx_, i, j, &v.ragged, &v.list_pos, &n_ints));
+					// 32-bit positions when the engine mirrored them that way (half the PCIe bytes), else the 64-bit array
+					if (tnsb_get_neighborlists_u32(ctx_, i, j, &v.ragged, &v.list_pos32, &n_ints) != TNSB_OK) {
+						v.list_pos32 = nullptr;
+						ok(tnsb_get_neighborlists(ctx_, i, j, &v.ragged, &v.list_pos, &n_ints));
+					}
 					views_[(size_t)i * (size_t)n_sets_ + (size_t)j] = v;
 				}
 			}

@@ -166,6 +166,11 @@ int tnsb_run(tnsb_context* ctx);
    reference's storage  [n, j0, j1, ..., j(n-1)]  (TreeNSearch.h:395).  Pointers stay valid until the next tnsb_run(). */
 int tnsb_get_neighborlists(const tnsb_context* ctx, int set_i, int set_j,
                            const int32_t** ragged, const int64_t** list_pos, int64_t* n_ints);
+/* same host view with 32-bit positions: list_pos travels over PCIe as uint32 while the list buffer holds fewer than 2^32 ints (half the
+   bytes; tnsb_get_neighborlists then widens it on the host the first time it is asked).  TNSB_ERR_LIMIT when the positions need 64 bits.
+   This is what include/tns/TreeNSearch.h reads (TreeNSearch.h:395 of the reference keeps one pointer per point instead). */
+int tnsb_get_neighborlists_u32(const tnsb_context* ctx, int set_i, int set_j,
+                               const int32_t** ragged, const uint32_t** list_pos32, int64_t* n_ints);
 /* same, device pointers (always available after tnsb_run(), also when TNSB_OPT_HOST_RESULTS == 0) */
 int tnsb_get_neighborlists_device(const tnsb_context* ctx, int set_i, int set_j,
                                   const int32_t** d_ragged, const int64_t** d_list_pos, int64_t* n_ints);

@@ -658,6 +658,27 @@ def test_speculative_grid_reuse_and_fallback(tnsb):
     assert_matches_port(e2, dict(sets=[(pts, rad)], radius=None, pairs=[(0, 0)], symmetric=True))
 
 
+def test_list_pos_32_bit_host_mirror(tnsb):
+    """The host mirror of list_pos travels as uint32 (tnsb_get_neighborlists_u32, what the C++ drop-in header reads); the 64-bit getter
+    widens it on the host on first use.  Same positions either way, run after run."""
+    import ctypes as C
+    case = cases.GOLDEN_CASES["uniform_fixed_5000"]()
+    eng = run_engine(tnsb, case)
+    n = case["sets"][0][0].shape[0]
+    for _ in range(3):
+        eng.run()
+        rag = C.POINTER(C.c_int32)()
+        p32 = C.POINTER(C.c_uint32)()
+        n_ints = C.c_int64()
+        eng._check(eng._lib.tnsb_get_neighborlists_u32(eng._h, 0, 0, C.byref(rag), C.byref(p32), C.byref(n_ints)))
+        pos32 = np.ctypeslib.as_array(p32, shape=(n,)).astype(np.int64)
+        eng._views.clear()
+        ragged, pos64 = eng.neighbor_lists(0, 0)
+        assert np.array_equal(pos32, np.asarray(pos64))
+        assert eng.stats()["d2h_bytes"] <= 4 * int(n_ints.value) + 4 * n
+    assert_matches_port(eng, case)
+
+
 def test_graph_replay_small_steady_state(tnsb):
     """Small problems in steady state: the enqueue phase of run() becomes ONE CUDA graph launch (captured once two consecutive runs
     looked alike, replayed while configuration / pointers / sizes / buffers are unchanged).  Moving points, host and device arrays,

@@ -79,6 +79,7 @@ SIGNATURES = {
     "tnsb_does_set_exist": (C.c_int, [_vp, C.c_int]),
     "tnsb_run": (C.c_int, [_vp]),
     "tnsb_get_neighborlists": (C.c_int, [_vp, C.c_int, C.c_int, _i32pp, _i64pp, C.POINTER(C.c_int64)]),
+    "tnsb_get_neighborlists_u32": (C.c_int, [_vp, C.c_int, C.c_int, _i32pp, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_int64)]),
     "tnsb_get_neighborlists_device": (C.c_int, [_vp, C.c_int, C.c_int, _i32pp, _i64pp, C.POINTER(C.c_int64)]),
     "tnsb_prepare_zsort": (C.c_int, [_vp]),
     "tnsb_get_zsort_order": (C.c_int, [_vp, C.c_int, _i32pp, C.POINTER(C.c_int)]),

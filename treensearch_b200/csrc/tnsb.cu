@@ -137,6 +137,12 @@ struct PairState {
     bool valid = false;
     bool host_valid = false;
     bool pos_copied = false;   // list_pos is already on its way to the host (enqueued right behind the query, before the counters are known)
+    // host mirror of list_pos as uint32 (half the PCIe bytes) while every position fits 32 bits; the int64 host array is then filled on
+    // the host, lazily, for callers of the 64-bit getter
+    DevBuf d_list_pos32;
+    PinBuf h_list_pos32;
+    bool pos32 = false;
+    bool host_pos64_valid = false;
 };
 
 enum Stage { EV_BEGIN = 0, EV_UPLOAD, EV_AABB, EV_KEYS, EV_SORT, EV_REORDER, EV_CELLS, EV_QUERY, EV_DOWNLOAD, EV_COUNT };
@@ -885,6 +891,13 @@ float ev_ms(tnsb_context* c, int a, int b)
 
 int run_impl(tnsb_context* c);
 
+// list_pos (int64, indexed by the kernels) -> uint32 for the host mirror
+__global__ void __launch_bounds__(256) pack_pos32_kernel(const long long* __restrict__ pos, uint32_t* __restrict__ out, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)pos[i];
+}
+
 // Everything the work enqueued by a steady-state run() depends on: configuration, borrowed pointers, sizes, the reused grid, every
 // engine buffer (through the allocation epoch).  Two runs with the same key enqueue the same kernels with the same arguments.
 std::vector<uint64_t> make_run_key(const tnsb_context* c)
@@ -966,7 +979,7 @@ int run_impl(tnsb_context* c)
 
     if (replay) {
         c->stats = c->graph_stats;
-        for (auto& p : c->pairs) { p.host_valid = false; p.n_ints = 0; p.n_neighbors = 0; }      // (pos_copied stays as the captured run left it)
+        for (auto& p : c->pairs) { p.host_valid = false; p.n_ints = 0; p.n_neighbors = 0; p.host_pos64_valid = !p.pos32; }      // (pos_copied / pos32 stay as the captured run left them)
         for (auto& hc : c->graph_host_copies) memcpy(hc.dst, hc.src, hc.bytes);
         act = c->graph_act;
         for (int id : act)
@@ -1069,8 +1082,21 @@ int run_impl(tnsb_context* c)
                 for (int id : todo) {
                     PairState& ps = c->pairs[id];
                     if (rc != TNSB_OK || ps.n_lists == 0) continue;
-                    if (ps.h_list_pos.ensure(sizeof(long long) * (size_t)c->sets[id / n_sets].n, 1.25) != cudaSuccess ||
-                        cudaMemcpyAsync(ps.h_list_pos.p, ps.d_list_pos.p, sizeof(long long) * (size_t)ps.n_lists, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = TNSB_ERR_CUDA;
+                    const size_t n_set = (size_t)c->sets[id / n_sets].n;
+                    ps.pos32 = ps.capacity < (int64_t)0xffffffffll;          // every position of this run fits 32 bits
+                    ps.host_pos64_valid = !ps.pos32;
+                    if (ps.h_list_pos.ensure(sizeof(long long) * n_set, 1.25) != cudaSuccess) rc = TNSB_ERR_CUDA;
+                    if (ps.pos32) {
+                        if (ps.d_list_pos32.ensure(sizeof(uint32_t) * n_set, 1.1) != cudaSuccess || ps.h_list_pos32.ensure(sizeof(uint32_t) * n_set, 1.25) != cudaSuccess) rc = TNSB_ERR_CUDA;
+                        if (rc == TNSB_OK) {
+                            pack_pos32_kernel<<<ceil_div(ps.n_lists, 256), 256, 0, s>>>(ps.d_list_pos.as<long long>(), ps.d_list_pos32.as<uint32_t>(), ps.n_lists);
+                            c->stats.n_kernel_launches++;
+                            if (cudaMemcpyAsync(ps.h_list_pos32.p, ps.d_list_pos32.p, sizeof(uint32_t) * (size_t)ps.n_lists, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = TNSB_ERR_CUDA;
+                        }
+                    } else if (rc == TNSB_OK &&
+                               cudaMemcpyAsync(ps.h_list_pos.p, ps.d_list_pos.p, sizeof(long long) * (size_t)ps.n_lists, cudaMemcpyDeviceToHost, s) != cudaSuccess) {
+                        rc = TNSB_ERR_CUDA;
+                    }
                     ps.pos_copied = true;
                 }
             }
@@ -1180,7 +1206,7 @@ int run_impl(tnsb_context* c)
             TNSB_CUDA(c, cudaMemcpyAsync(ps.h_ragged.p, ps.d_ragged.p, sizeof(int32_t) * (size_t)ps.n_ints, cudaMemcpyDeviceToHost, s));
         }
         if (!ps.pos_copied) TNSB_CUDA(c, cudaMemcpyAsync(ps.h_list_pos.p, ps.d_list_pos.p, sizeof(long long) * (size_t)ps.n_lists, cudaMemcpyDeviceToHost, s));
-        c->stats.d2h_bytes += (int64_t)sizeof(int32_t) * ps.n_ints + (int64_t)sizeof(long long) * ps.n_lists;
+        c->stats.d2h_bytes += (int64_t)sizeof(int32_t) * ps.n_ints + (int64_t)(ps.pos32 ? sizeof(uint32_t) : sizeof(long long)) * ps.n_lists;
         ps.host_valid = true;
     }
     TNSB_EVENT(c, cudaEventRecord(c->ev[EV_DOWNLOAD], s));
@@ -1289,7 +1315,7 @@ void tnsb_destroy(tnsb_context* c)
         st.sorted.release(); st.sorted_r2.release(); st.cell_key.release(); st.cell_start.release(); st.tile_heads.release();
         st.htable.release(); st.dense.release(); st.first.release(); st.cursor.release(); st.d_zorder.release(); st.h_zorder.release();
     }
-    for (auto& p : c->pairs) { p.d_ragged.release(); p.d_list_pos.release(); p.d_tasks.release(); p.h_ragged.release(); p.h_list_pos.release(); }
+    for (auto& p : c->pairs) { p.d_ragged.release(); p.d_list_pos.release(); p.d_tasks.release(); p.h_ragged.release(); p.h_list_pos.release(); p.d_list_pos32.release(); p.h_list_pos32.release(); }
     for (int p = 0; p < 2; p++) {
         for (int r = 0; r < (int)c->win_peer[p].size(); r++)
             if (r != c->win_rank && c->win_peer[p][r]) cudaIpcCloseMemHandle(c->win_peer[p][r]);
@@ -1499,8 +1525,39 @@ int tnsb_get_neighborlists(const tnsb_context* c, int si, int sj, const int32_t*
         const_cast<tnsb_context*>(c)->err = "tnsb: host results are disabled (TNSB_OPT_HOST_RESULTS = 0); use tnsb_get_neighborlists_device.";
         return TNSB_ERR_INVALID_STATE;
     }
+    if (list_pos && ps.pos32 && !ps.host_pos64_valid && ps.n_lists > 0) {
+        // the positions came over PCIe as uint32 (tnsb_get_neighborlists_u32 hands those out): widen them once for this caller
+        PairState& m = const_cast<tnsb_context*>(c)->pairs[id];
+        const uint32_t* src = m.h_list_pos32.as<uint32_t>();
+        int64_t* dst = m.h_list_pos.as<int64_t>();
+        for (int i = 0; i < m.n_lists; i++) dst[i] = (int64_t)src[i];
+        m.host_pos64_valid = true;
+    }
     if (ragged) *ragged = ps.h_ragged.as<int32_t>();
     if (list_pos) *list_pos = ps.h_list_pos.as<int64_t>();
+    if (n_ints) *n_ints = ps.n_ints;
+    return TNSB_OK;
+}
+
+int tnsb_get_neighborlists_u32(const tnsb_context* c, int si, int sj, const int32_t** ragged, const uint32_t** list_pos32, int64_t* n_ints)
+{
+    if (!c || si < 0 || sj < 0 || si >= (int)c->sets.size() || sj >= (int)c->sets.size()) return TNSB_ERR_INVALID_ARGUMENT;
+    const size_t id = (size_t)si * c->sets.size() + sj;
+    if (id >= c->pairs.size() || !c->pairs[id].valid) {
+        const_cast<tnsb_context*>(c)->err = "TreeNSearch::get_neighborlist error: Set pair not active (or run() not called).";
+        return TNSB_ERR_INVALID_STATE;
+    }
+    const PairState& ps = c->pairs[id];
+    if (ps.n_lists > 0 && !ps.host_valid) {
+        const_cast<tnsb_context*>(c)->err = "tnsb: host results are disabled (TNSB_OPT_HOST_RESULTS = 0); use tnsb_get_neighborlists_device.";
+        return TNSB_ERR_INVALID_STATE;
+    }
+    if (ps.n_lists > 0 && !ps.pos32) {
+        const_cast<tnsb_context*>(c)->err = "tnsb: the list buffer of this pair exceeds 2^32 ints; use tnsb_get_neighborlists (64-bit positions).";
+        return TNSB_ERR_LIMIT;
+    }
+    if (ragged) *ragged = ps.h_ragged.as<int32_t>();
+    if (list_pos32) *list_pos32 = ps.h_list_pos32.as<uint32_t>();
     if (n_ints) *n_ints = ps.n_ints;
     return TNSB_OK;
 }
