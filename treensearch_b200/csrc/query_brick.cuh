@@ -377,14 +377,14 @@ __device__ __noinline__ void brick_slow_query(const BrickArgs& a, float qx, floa
 
 
 // slow path of a STAGED brick (the list does not fit the hit column, or the query has more than kMaxTot candidates): one query, the
-// whole warp, candidates from the slab in shared memory (all 25 rows, +-2 cells, no culling), count pass + fill pass
+// whole warp, candidates from the slab in shared memory (all 25 rows, +-2 cells, no culling).  The hits of the first pass are kept in
+// the warp's scratch: a list that fits it is written out -- sorted if asked -- without a second pass.
 template <bool SYMMETRIC>
 __device__ __noinline__ void brick_slow_query_staged(const BrickArgs& a, uint32_t slab_a, uint32_t r2_a, const uint16_t* tq, float qx, float qy, float qz, int qid,
                                                     float r2, int self_off, int lane, unsigned& nb_sum, uint32_t scratch_a, int scratch_cap)
 {
     const unsigned lt = lanemask_lt();
     int32_t* dst = nullptr;
-    bool to_scratch = false;
     int n_list = 0;
     for (int pass = 0; pass < 2; pass++) {
         int n = 0;
@@ -403,9 +403,10 @@ __device__ __noinline__ void brick_slow_query_staged(const BrickArgs& a, uint32_
                     if (SYMMETRIC) hit = hit || (d2 <= lds_f32(r2_a + (t >> 2)));
                 }
                 const unsigned m = __ballot_sync(kFull, hit);
-                if (pass == 1 && hit) {
-                    if (to_scratch) sts_u32(scratch_a + (uint32_t)(n + __popc(m & lt)) * 4u, (uint32_t)id);
-                    else dst[1 + n + __popc(m & lt)] = id;
+                if (hit) {
+                    const int k = n + __popc(m & lt);
+                    if (pass == 1) dst[1 + k] = id;
+                    else if (k < scratch_cap) sts_u32(scratch_a + (uint32_t)k * 4u, (uint32_t)id);
                 }
                 n += __popc(m);
             }
@@ -426,21 +427,22 @@ __device__ __noinline__ void brick_slow_query_staged(const BrickArgs& a, uint32_
             }
             nb_sum += (unsigned)n;
             n_list = n;
-            to_scratch = a.sort_lists && n <= scratch_cap;      // ascending ids: the list is sorted in shared memory before it leaves the SM
+            if (n <= scratch_cap) {
+                // the whole list sits in the scratch: sort it there, one coalesced copy, done
+                __syncwarp();
+                if (a.sort_lists && n > 1)
+                    warp_bitonic_sort(n, lane, [&](int i) { return (int)lds_u32(scratch_a + (uint32_t)i * 4u); }, [&](int i, int x) { sts_u32(scratch_a + (uint32_t)i * 4u, (uint32_t)x); });
+                for (int i = lane; i < n; i += 32) dst[1 + i] = (int)lds_u32(scratch_a + (uint32_t)i * 4u);
+                __syncwarp();
+                return;
+            }
         }
     }
     if (a.sort_lists && n_list > 1) {
+        // longer than the warp's scratch (thousands of neighbours): in place, in the ragged buffer
         __syncwarp();
-        if (to_scratch) {
-            warp_bitonic_sort(n_list, lane, [&](int i) { return (int)lds_u32(scratch_a + (uint32_t)i * 4u); }, [&](int i, int v) { sts_u32(scratch_a + (uint32_t)i * 4u, (uint32_t)v); });
-            for (int i = lane; i < n_list; i += 32) dst[1 + i] = (int)lds_u32(scratch_a + (uint32_t)i * 4u);
-        } else {
-            // longer than the warp's scratch (thousands of neighbours): in place, in global memory
-            volatile int32_t* v = dst + 1;
-            warp_bitonic_sort(n_list, lane, [&](int i) { return (int)v[i]; }, [&](int i, int x) { v[i] = x; });
-        }
-    } else if (to_scratch && n_list == 1) {
-        if (lane == 0) dst[1] = (int)lds_u32(scratch_a);
+        volatile int32_t* v = dst + 1;
+        warp_bitonic_sort(n_list, lane, [&](int i) { return (int)v[i]; }, [&](int i, int x) { v[i] = x; });
     }
 }
 
