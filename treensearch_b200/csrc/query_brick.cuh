@@ -657,8 +657,16 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
                 float4 q = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0x7fffffff));
                 float r2 = a.r2_fixed;
                 if (has) {
-                    q = a.q.pts[qp];
-                    if (VARIABLE) r2 = a.q.r2[qp];
+                    if (same_set && staged) {
+                        // the query's own row is part of the staged slab: its record is read from shared memory (a global load here is a
+                        // full L2 / DRAM round trip at the head of every task, with 16 warps per SM to hide it)
+                        const uint32_t qoff = (uint32_t)(qp + (int)meta[44 + rr]) * 16u;
+                        q = lds_f4(slab_a + qoff);
+                        if (VARIABLE) r2 = SYMMETRIC ? lds_f32(buf_a + SM::kOffR2 + (qoff >> 2)) : a.q.r2[qp];
+                    } else {
+                        q = a.q.pts[qp];
+                        if (VARIABLE) r2 = a.q.r2[qp];
+                    }
                 }
                 const int qid = __float_as_int(q.w);
                 const bool active = has && qid < query_limit;
