@@ -81,6 +81,11 @@ struct BrickArgs {
     int* max_list;            // longest list written (atomicMax): picks the hit column height of the next run
     int host_out;             // the ragged buffer is mapped host memory: lists leave the SM as aligned, fully coalesced 128-byte stores
     int sort_lists;           // ascending neighbour ids inside every list (the reference's order)
+    // lists longer than a warp's scratch that must be sorted AND live in mapped host memory are built and sorted in this device buffer
+    // first (a bump allocator per run), then copied out: sorting them in place would be a PCIe round trip per compare-exchange
+    int32_t* long_scratch;
+    unsigned long long* long_cursor;
+    long long long_cap;
     int* overflow;
 };
 
@@ -285,6 +290,34 @@ __device__ __forceinline__ void warp_bitonic_sort(int n, int lane, Load ld, Stor
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
+// where the second pass of a slow path writes a list of n ids that did not fit the warp's scratch: straight behind its count word in the
+// ragged buffer, or -- sorted lists in mapped host memory -- into a piece of the device scratch (nullptr: none left, sort in place)
+__device__ __forceinline__ int32_t* long_list_target(const BrickArgs& a, int32_t* dst, int n, int lane, bool& staged_out)
+{
+    staged_out = false;
+    if (!(a.host_out && a.sort_lists && a.long_scratch)) return dst + 1;
+    unsigned long long at = 0;
+    if (lane == 0) at = atomicAdd(a.long_cursor, (unsigned long long)n);
+    at = __shfl_sync(kFull, at, 0);
+    if ((long long)(at + (unsigned long long)n) > a.long_cap) return dst + 1;
+    staged_out = true;
+    return a.long_scratch + at;
+}
+
+// sorts the n ids at `wr` (device memory) and, when they were staged, copies them behind the count word at dst
+__device__ __forceinline__ void long_list_finish(const BrickArgs& a, int32_t* dst, int32_t* wr, int n, int lane, bool staged_out)
+{
+    __syncwarp();
+    if (a.sort_lists && n > 1) {
+        volatile int32_t* v = wr;
+        warp_bitonic_sort(n, lane, [&](int i) { return (int)v[i]; }, [&](int i, int x) { v[i] = x; });
+    }
+    if (staged_out) {
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) dst[1 + i] = wr[i];
+    }
+}
+
 // slow path: one query, the whole warp, candidates from global memory.  The 25 row bounds are fetched by 25 lanes at once, the rows are
 // walked with FOUR warp-wide candidate loads in flight (the path is bound by memory latency, not by arithmetic), and the hits of the
 // first pass are kept in the warp's scratch: a list that fits it (<= scratch_cap ids) is written out -- sorted if asked -- without a second
@@ -304,6 +337,8 @@ __device__ __noinline__ void brick_slow_query(const BrickArgs& a, float qx, floa
         }
     }
     int32_t* dst = nullptr;
+    int32_t* wr = nullptr;
+    bool staged_out = false;
     int n_list = 0;
     for (int pass = 0; pass < 2; pass++) {
         int n = 0;
@@ -333,7 +368,7 @@ __device__ __noinline__ void brick_slow_query(const BrickArgs& a, float qx, floa
                     const unsigned m = __ballot_sync(kFull, hit);
                     if (hit) {
                         const int k = n + __popc(m & lt);
-                        if (pass == 1) dst[1 + k] = id;
+                        if (pass == 1) wr[k] = id;
                         else if (k < scratch_cap) sts_u32(scratch_a + (uint32_t)k * 4u, (uint32_t)id);
                     }
                     n += __popc(m);
@@ -365,14 +400,11 @@ __device__ __noinline__ void brick_slow_query(const BrickArgs& a, float qx, floa
                 __syncwarp();
                 return;
             }
+            wr = long_list_target(a, dst, n, lane, staged_out);
         }
     }
-    if (a.sort_lists && n_list > 1) {
-        // longer than the warp's scratch (thousands of neighbours): in place, in the ragged buffer
-        __syncwarp();
-        volatile int32_t* v = dst + 1;
-        warp_bitonic_sort(n_list, lane, [&](int i) { return (int)v[i]; }, [&](int i, int x) { v[i] = x; });
-    }
+    // longer than the warp's scratch (thousands of neighbours): sorted in device memory
+    long_list_finish(a, dst, wr, n_list, lane, staged_out);
 }
 
 
@@ -385,6 +417,8 @@ __device__ __noinline__ void brick_slow_query_staged(const BrickArgs& a, uint32_
 {
     const unsigned lt = lanemask_lt();
     int32_t* dst = nullptr;
+    int32_t* wr = nullptr;
+    bool staged_out = false;
     int n_list = 0;
     for (int pass = 0; pass < 2; pass++) {
         int n = 0;
@@ -405,7 +439,7 @@ __device__ __noinline__ void brick_slow_query_staged(const BrickArgs& a, uint32_
                 const unsigned m = __ballot_sync(kFull, hit);
                 if (hit) {
                     const int k = n + __popc(m & lt);
-                    if (pass == 1) dst[1 + k] = id;
+                    if (pass == 1) wr[k] = id;
                     else if (k < scratch_cap) sts_u32(scratch_a + (uint32_t)k * 4u, (uint32_t)id);
                 }
                 n += __popc(m);
@@ -436,14 +470,11 @@ __device__ __noinline__ void brick_slow_query_staged(const BrickArgs& a, uint32_
                 __syncwarp();
                 return;
             }
+            wr = long_list_target(a, dst, n, lane, staged_out);
         }
     }
-    if (a.sort_lists && n_list > 1) {
-        // longer than the warp's scratch (thousands of neighbours): in place, in the ragged buffer
-        __syncwarp();
-        volatile int32_t* v = dst + 1;
-        warp_bitonic_sort(n_list, lane, [&](int i) { return (int)v[i]; }, [&](int i, int x) { v[i] = x; });
-    }
+    // longer than the warp's scratch (thousands of neighbours): sorted in device memory
+    long_list_finish(a, dst, wr, n_list, lane, staged_out);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------

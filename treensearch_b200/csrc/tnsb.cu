@@ -79,6 +79,7 @@ struct PairCounters {
     uint32_t n_tasks;
     int plan_overflow;
     unsigned long long n_slow;
+    unsigned long long long_cursor;   // bump allocator of the long-list scratch (brick query slow paths)
     int max_list;
     int pad_;
 };
@@ -207,6 +208,7 @@ struct tnsb_context {
     BrickGrid bgrid;
 
     DevBuf d_reduce;        // 8 x uint32
+    DevBuf d_long_scratch;  // brick query: long sorted lists bound for mapped host memory are built and sorted here first (64 MB, on first use)
     DevBuf d_counters;      // PairCounters per pair
     DevBuf d_misc;          // n_cells per set (uint32)
     DevBuf sort_temp, scan_temp;
@@ -664,6 +666,14 @@ int query_pair_brick(tnsb_context* c, int si, int sj, PairCounters* d_cnt)
     a.n_neighbors = &d_cnt->n_neighbors;
     a.n_slow = &d_cnt->n_slow;
     a.max_list = &d_cnt->max_list;
+    a.long_scratch = nullptr;
+    a.long_cursor = &d_cnt->long_cursor;
+    a.long_cap = 0;
+    if (ps.in_host && (c->opt_sort_lists == 1 || (c->opt_sort_lists < 0 && c->opt_host_results))) {
+        TNSB_CUDA(c, c->d_long_scratch.ensure((size_t)64 << 20));
+        a.long_scratch = c->d_long_scratch.as<int32_t>();
+        a.long_cap = (long long)(c->d_long_scratch.cap / sizeof(int32_t));
+    }
     a.host_out = ps.in_host ? 1 : 0;
     a.sort_lists = c->opt_sort_lists == 1 || (c->opt_sort_lists < 0 && c->opt_host_results) ? 1 : 0;
     a.overflow = &d_cnt->overflow;
@@ -1321,7 +1331,7 @@ void tnsb_destroy(tnsb_context* c)
             if (r != c->win_rank && c->win_peer[p][r]) cudaIpcCloseMemHandle(c->win_peer[p][r]);
         c->win[p].release();
     }
-    c->d_reduce.release(); c->d_counters.release(); c->d_misc.release(); c->sort_temp.release(); c->scan_temp.release(); c->h_small.release();
+    c->d_long_scratch.release(); c->d_reduce.release(); c->d_counters.release(); c->d_misc.release(); c->sort_temp.release(); c->scan_temp.release(); c->h_small.release();
     for (int k = 0; k < EV_COUNT; k++) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
