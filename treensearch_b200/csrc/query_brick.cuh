@@ -43,6 +43,10 @@ constexpr int kTabH = 32;                                // per-lane range table
 constexpr int kMaxTot = 1024;                            // candidates per query on the fast path (variable radii: cells of r_max / 2 hold many candidates of a small query)
 constexpr int kColStride = 68;                           // bytes between consecutive hits of one lane (34 uint16: conflict-free column reads)
 constexpr uint32_t kBrickSlow = 1u << 24;                // task flag: single cell whose slab does not fit
+constexpr uint32_t kSlowPart = 64;                       // queries per task of such a cell: a dense cell becomes many tasks, i.e. many CTAs
+constexpr uint32_t kBrickPart = 1u << 25;                // task flag: a HEAVY staged brick (dense cells: its queries all take the warp-cooperative path) is
+                                                         // handed out several times, kSlowPart queries per task (part index in z0 >> 21): every CTA stages the
+                                                         // (small) slab again, the queries spread over the GPU instead of queueing in one CTA
 
 struct BrickTask {
     int x0, y0, z0;
@@ -98,7 +102,7 @@ struct BrickSmem {
     static constexpr int kOffT = kOffR2 + (SYM ? (SLAB + kDummy) * 4 : 0);
     static constexpr int kOffMeta = kOffT + ((kSlabRows * kTW * 2 + 15) & ~15);
     // meta words: [0] x0 [1] y0 [2] z0 [3] dims | flags [4] n queries [5] staged [6] next warp task [7] end
-    //             [8, 24) qs   [24, 41) qoff   [41] queries per warp task   [44, 60) qdelta
+    //             [8, 24) qs   [24, 41) qoff   [41] queries per warp task   [42] first query of the task   [44, 60) qdelta
     static constexpr int kMetaWords = 64;
     static constexpr int kOffRowKey = kOffMeta + kMetaWords * 4;        // producer scratch: key of the first cell of every slab row
     static constexpr int kOffRowBase = kOffRowKey + kSlabRows * 4;      //                   slab position - global position of the row's records
@@ -196,16 +200,20 @@ __device__ __forceinline__ int brick_cell(float v, double bottom, double inv_cel
 // ---------------------------------------------------------------------------------------------------------------------------
 // Plan: one warp per 32 x 4 x 4 brick; bricks without queries are dropped, bricks whose candidate slab exceeds slab_cap are
 // split (x first: rows stay long) down to single cells, which are flagged for the slow path.
-__device__ __forceinline__ uint32_t plan_rows(const uint32_t* first, const BrickGrid& g, int xa, int xb, int y0, int ny_rows, int z0, int nz_rows, int lane)
+__device__ __forceinline__ uint32_t plan_rows(const uint32_t* first, const BrickGrid& g, int xa, int xb, int y0, int ny_rows, int z0, int nz_rows, int lane,
+                                              uint32_t* row_max = nullptr)
 {
-    uint32_t s = 0;
+    uint32_t s = 0, m = 0;
     const int n_rows = ny_rows * nz_rows;
     for (int r = lane; r < n_rows; r += 32) {
         const int y = y0 + r % ny_rows, z = z0 + r / ny_rows;
         if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
         const uint32_t key0 = ((uint32_t)z * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nx;
-        s += first[key0 + xb] - first[key0 + xa];
+        const uint32_t c = first[key0 + xb] - first[key0 + xa];
+        s += c;
+        m = max(m, c);
     }
+    if (row_max) *row_max = __reduce_max_sync(kFull, m);
     return __reduce_add_sync(kFull, s);
 }
 
@@ -231,7 +239,8 @@ __global__ void __launch_bounds__(256) brick_plan_kernel(const BrickGrid g, cons
             __syncwarp();
             const uint32_t nq = plan_rows(q_first, g, x0, x0 + ex, y0, ey, z0, ez, lane);
             if (nq == 0) continue;
-            const uint32_t nc = plan_rows(c_first, g, max(x0 - 2, 0), min(x0 + ex + 2, g.nx), y0 - 2, ey + 4, z0 - 2, ez + 4, lane);
+            uint32_t row_max = 0;
+            const uint32_t nc = plan_rows(c_first, g, max(x0 - 2, 0), min(x0 + ex + 2, g.nx), y0 - 2, ey + 4, z0 - 2, ez + 4, lane, &row_max);
             uint32_t flags = 0;
             if (nc > (uint32_t)slab_cap) {
                 if (ex > 1 || ey > 1 || ez > 1) {
@@ -250,14 +259,23 @@ __global__ void __launch_bounds__(256) brick_plan_kernel(const BrickGrid g, cons
                 flags = kBrickSlow;
             }
             if (lane == 0) {
-                const uint32_t id = atomicAdd(n_tasks, 1u);
-                if (id < max_tasks) {
-                    BrickTask t;
-                    t.x0 = x0; t.y0 = y0; t.z0 = z0;
-                    t.dims = (uint32_t)ex | ((uint32_t)ey << 8) | ((uint32_t)ez << 16) | flags;
-                    tasks[id] = t;
-                } else {
-                    *plan_overflow = 1;
+                // an unstageable cell is cut into tasks of kSlowPart queries (its queries read their candidates from global memory, nothing
+                // is shared through the slab): dims = 1 | part << 8 | kBrickSlow
+                // a staged brick is heavy when its queries will mostly exceed kMaxTot candidates: cells so full that an average query does
+                // (125 cells per query), or one row of the slab that alone holds hundreds of records (a blob inside an otherwise sparse brick)
+                const uint32_t slab_cells = (uint32_t)((ex + 4) * (ey + 4) * (ez + 4));
+                const bool heavy = !flags && nq > kSlowPart && ((unsigned long long)nc * 125ull > (unsigned long long)kMaxTot * slab_cells || row_max >= 400u);
+                const uint32_t parts = flags ? min((nq + kSlowPart - 1u) / kSlowPart, 0xffffu) : (heavy ? min((nq + kSlowPart - 1u) / kSlowPart, 0x7ffu) : 1u);
+                const uint32_t id = atomicAdd(n_tasks, parts);
+                for (uint32_t p = 0; p < parts; p++) {
+                    if (id + p < max_tasks) {
+                        BrickTask t;
+                        t.x0 = x0; t.y0 = y0; t.z0 = heavy ? (int)((uint32_t)z0 | (p << 21)) : z0;
+                        t.dims = flags ? (1u | (p << 8) | flags) : ((uint32_t)ex | ((uint32_t)ey << 8) | ((uint32_t)ez << 16) | (heavy ? kBrickPart : 0u));
+                        tasks[id + p] = t;
+                    } else {
+                        *plan_overflow = 1;
+                    }
                 }
             }
         }
@@ -530,9 +548,12 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
                 break;
             }
             const BrickTask bt = a.tasks[task];
-            const int x0 = bt.x0, y0 = bt.y0, z0 = bt.z0;
-            const int ex = (int)(bt.dims & 0xffu), ey = (int)((bt.dims >> 8) & 0xffu), ez = (int)((bt.dims >> 16) & 0xffu);
+            const bool part_brick = (bt.dims & kBrickPart) != 0;
+            const int x0 = bt.x0, y0 = bt.y0, z0 = part_brick ? (int)((uint32_t)bt.z0 & 0x1fffffu) : bt.z0;
+            const uint32_t brick_part = part_brick ? ((uint32_t)bt.z0 >> 21) : 0u;
             const bool slow_brick = (bt.dims & kBrickSlow) != 0;
+            const int ex = (int)(bt.dims & 0xffu), ey = slow_brick ? 1 : (int)((bt.dims >> 8) & 0xffu), ez = slow_brick ? 1 : (int)((bt.dims >> 16) & 0xffu);
+            const uint32_t slow_part = (bt.dims >> 8) & 0xffffu;          // unstageable cell: which kSlowPart queries of it
             const int tw = ex + 5;
             const int xa = max(x0 - 2, 0), xb = min(x0 + ex + 2, g.nx);
             // slab rows: rows lane and lane + 32 (row = sz * 8 + sy)
@@ -559,6 +580,11 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
                     const uint32_t key0 = ((uint32_t)(z0 + rz) * (uint32_t)g.ny + (uint32_t)(y0 + ry)) * (uint32_t)g.nx;
                     qs = a.q.first[key0 + x0];
                     qcnt = a.q.first[key0 + x0 + ex] - qs;
+                    if (slow_brick) {
+                        const uint32_t o = min(qcnt, slow_part * kSlowPart);
+                        qs += o;
+                        qcnt = slow_part == 0xfffeu ? qcnt - o : min(qcnt - o, kSlowPart);     // the last representable part (the planner emits at most 0xffff) takes the rest
+                    }
                 }
             }
             const uint32_t inc0 = (uint32_t)warp_inclusive_scan((int)len[0], lane);
@@ -579,12 +605,16 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
             if (lane == kQRows) meta[24 + lane] = nq_all;
             if (lane == 0) {
                 meta[0] = (uint32_t)x0; meta[1] = (uint32_t)y0; meta[2] = (uint32_t)z0; meta[3] = bt.dims;
-                meta[4] = nq_all; meta[5] = staged ? 1u : 0u; meta[6] = 0u; meta[7] = 0u;
+                // queries [q_lo, q_hi) of the brick belong to this task (all of them, or one part of a heavy brick)
+                const uint32_t q_lo = part_brick ? min(nq_all, brick_part * kSlowPart) : 0u;
+                const uint32_t q_hi = part_brick ? (brick_part == 0x7feu ? nq_all : min(nq_all, q_lo + kSlowPart)) : nq_all;
+                const uint32_t nq_task = q_hi - q_lo;
+                meta[4] = q_hi; meta[42] = q_lo; meta[5] = staged ? 1u : 0u; meta[6] = 0u; meta[7] = 0u;
                 // queries per warp task: 32 -- or, for a brick with few queries and a heavy slab (dense neighbourhoods: long walks, lists
                 // that overflow into the warp-cooperative paths), as few as it takes to give every consumer warp a share of the brick:
                 // only two bricks are in flight per SM, so a brick that is one task would leave all other consumer warps idle
                 uint32_t tq = 32u;
-                if ((slow_brick || (total >= 1024u && total >= 8u * nq_all)) && nq_all < 32u * (uint32_t)NCONS) tq = max((nq_all + (uint32_t)NCONS - 1u) / (uint32_t)NCONS, 1u);
+                if ((slow_brick || (total >= 1024u && total >= 8u * nq_task)) && nq_task < 32u * (uint32_t)NCONS) tq = max((nq_task + (uint32_t)NCONS - 1u) / (uint32_t)NCONS, 1u);
                 meta[41] = tq;
             }
             __syncwarp();
@@ -667,7 +697,8 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
             const int x0 = (int)meta[0], y0 = (int)meta[1], z0 = (int)meta[2];
             const int ex = (int)(meta[3] & 0xffu);
             const bool staged = meta[5] != 0u;
-            const int nq = (int)meta[4];
+            const int nq = (int)meta[4];           // end of this task's queries (brick-local numbering)
+            const int q_lo = (int)meta[42];        // their start (0 unless the task is one part of a heavy brick)
             const int tqs = (int)meta[41];
             const uint32_t slab_a = buf_a + SM::kOffSlab;
 
@@ -675,8 +706,8 @@ __global__ void __launch_bounds__((NCONS + 2) * 32, 1) brick_query_kernel(const 
                 int wt = 0;
                 if (lane == 0) wt = (int)atomicAdd(&meta[6], 1u);
                 wt = __shfl_sync(kFull, wt, 0);
-                if (wt * tqs >= nq) break;
-                const int ci = wt * tqs + lane;
+                if (q_lo + wt * tqs >= nq) break;
+                const int ci = q_lo + wt * tqs + lane;
                 const bool has = lane < tqs && ci < nq;
                 // query row of this lane: last row whose first query is <= ci (binary search over the 16 row offsets)
                 int rr = (ci >= (int)meta[24 + 8]) ? 8 : 0;
