@@ -574,6 +574,21 @@ def run_ours(args):
         extras[f"{other}_input"] = {"ms_per_step": ms_other, "value": total / (ms_other * 1e-3) / 1e6, "unit": UNIT,
                                     "note": "every rank holds an i.i.d. sample of the cube: a step redistributes (N-1)/N of all points" if other == "random" else "every rank holds its own Z slab"}
         del job2
+        # (1b) clustered arm (north_star: "uniform and clustered clouds at 1/2/4/8 GPUs"): density gradient z -> z^1.5 along the slab axis
+        if args.workload == "uniform":
+            try:
+                job3 = sharded.ShardedUniformJob("clustered", args.points_per_gpu, rank, world, local_rank, stream, "slab")
+                ms_cl, _ = timer.run(job3.step_device, max(1, min(args.steps, 5)), 3)
+                st3 = job3.stats()
+                cnt3 = torch.tensor([st3["n_neighbors"], job3.search.n_owned, st3["n_slow_queries"]], dtype=torch.int64, device="cuda")
+                dist.all_reduce(cnt3, op=dist.ReduceOp.SUM)
+                extras["clustered_z15"] = {"ms_per_step": ms_cl, "value": total / (ms_cl * 1e-3) / 1e6, "unit": UNIT,
+                                           "neighbors_per_query": float(cnt3[0].item()) / max(float(cnt3[1].item()), 1.0), "n_slow_queries": int(cnt3[2].item()),
+                                           "note": "same point count, z -> 1e-3 + z^1.5: density gradient along the slab axis (up to 44x the mean at the dense end), "
+                                                   "count-balanced slabs of unequal thickness, same radius as the uniform arm"}
+                del job3
+            except Exception as e:      # noqa: BLE001
+                extras["clustered_z15"] = {"error": repr(e)[:300]}
         # (2) parity gate + strong scaling: rank 0 searches the WHOLE cloud on one GPU; neighbour totals and list digests of a sample of
         #     every rank's owned points must agree with it
         job.step_device()

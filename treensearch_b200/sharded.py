@@ -282,11 +282,18 @@ class ShardedUniformJob:
         import torch.distributed as dist
         from . import clouds
         total = points_per_gpu * world
-        if workload != "uniform":
-            raise SystemExit("multi-GPU bench supports the uniform workload")
+        if workload not in ("uniform", "clustered"):
+            raise SystemExit("multi-GPU bench supports the uniform and the clustered workload")
         self.radius = float(clouds.radius_for_mean_neighbors(total))
         chunk = clouds.uniform_cloud(points_per_gpu, 42 + rank)          # i.i.d. uniform chunk of the global cloud
-        if shard_input == "slab":
+        if workload == "clustered":
+            # density gradient along the slab axis: z -> z^1.5 of the GLOBAL coordinate (the density grows like z^(-1/3) towards z = 0, the
+            # count-balanced slabs get unequal thickness, the lowest slab holds the dense end with its long lists).  z is kept >= 1e-3
+            # (44x the mean density at most) so that the workload stays a clustered cloud and not a stress test of a singularity.
+            chunk = chunk.copy()
+            zg = (chunk[:, 2].astype(np.float64) + rank) / world if shard_input == "slab" else chunk[:, 2].astype(np.float64)
+            chunk[:, 2] = (1e-3 + (1.0 - 1e-3) * zg ** 1.5).astype(np.float32)
+        elif shard_input == "slab":
             # the cloud is ALREADY sharded by Z slab, as in a running simulation: rank r holds z in [r/world, (r+1)/world).  A step then
             # exchanges the one-cell halo plus the few points that the count-balanced cuts move across a boundary.  "random" hands
             # every rank an i.i.d. sample of the whole cube instead: (world-1)/world of all points change rank in every step.
