@@ -585,7 +585,7 @@ def run_ours(args):
                 extras["clustered_z15"] = {"ms_per_step": ms_cl, "value": total / (ms_cl * 1e-3) / 1e6, "unit": UNIT,
                                            "neighbors_per_query": float(cnt3[0].item()) / max(float(cnt3[1].item()), 1.0), "n_slow_queries": int(cnt3[2].item()),
                                            "note": "same point count, z -> 1e-3 + z^1.5: density gradient along the slab axis (up to 44x the mean at the dense end), "
-                                                   "count-balanced slabs of unequal thickness, same radius as the uniform arm"}
+                                                   "slab cuts weighted by the estimated cost per histogram bin (sharded.cost_weights: the dense end owns fewer points), same radius as the uniform arm"}
                 del job3
             except Exception as e:      # noqa: BLE001
                 extras["clustered_z15"] = {"error": repr(e)[:300]}

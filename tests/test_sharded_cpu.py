@@ -116,6 +116,24 @@ def test_balanced_cuts_properties():
     assert np.all(np.diff(cuts[1:-1]) >= 0)
 
 
+def test_cost_weighted_cuts():
+    """cost_weights: a uniform histogram keeps the count-balanced cuts; a density gradient moves the cuts so that the dense end gets
+    fewer points and every part about the same weight."""
+    uniform = np.full(4096, 250, np.int64)
+    assert np.array_equal(sharded.balanced_cuts(uniform, 0.0, 1.0, 8), sharded.balanced_cuts(uniform, 0.0, 1.0, 8, sharded.cost_weights(uniform)))
+    z = (np.random.RandomState(1).random_sample(1_000_000) ** 1.5)
+    hist = np.histogram(z, bins=4096, range=(0.0, 1.0))[0]
+    w = sharded.cost_weights(hist)
+    cuts = sharded.balanced_cuts(hist, 0.0, 1.0, 8, w)
+    assert cuts[0] == -np.inf and cuts[-1] == np.inf and np.all(np.diff(cuts[1:-1]) >= 0)
+    edges = np.concatenate([[0], np.round(cuts[1:-1] * 4096).astype(int), [4096]])
+    per_w = np.array([w[a:b].sum() for a, b in zip(edges[:-1], edges[1:])])
+    per_n = np.array([hist[a:b].sum() for a, b in zip(edges[:-1], edges[1:])])
+    assert per_w.max() - per_w.min() <= 2 * w.max() + 1e-9
+    assert per_n[0] < per_n[-1]                      # the dense end (z -> 0) owns fewer points than the sparse end
+    assert per_n.sum() == hist.sum()
+
+
 def test_single_rank_exchange_is_identity():
     rec = torch.arange(40, dtype=torch.float32).reshape(10, 4)
     counts = np.array([7, 3], dtype=np.int64)

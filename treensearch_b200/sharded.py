@@ -34,19 +34,30 @@ import numpy as np
 from . import _lib as L
 
 
-def balanced_cuts(hist: np.ndarray, lo: float, hi: float, n_parts: int) -> np.ndarray:
-    """Cut coordinates (float32, length n_parts + 1) such that every part holds ~ the same number of points.
+def cost_weights(hist: np.ndarray) -> np.ndarray:
+    """Work estimate per histogram bin for the cut placement: a bin of c points along the slab axis (uniform cross-section) has density
+    ~ c, and a point's search cost grows with the density around it, so the work of the bin grows like c * (1 + c / mean) -- points
+    where the cloud is as dense as on average, pairs where it is much denser.  A uniform cloud gets the count-balanced cuts."""
+    h = np.asarray(hist, dtype=np.float64)
+    occupied = h[h > 0]
+    mean = float(occupied.mean()) if occupied.size else 1.0
+    return h * (1.0 + h / mean) * 0.5
+
+
+def balanced_cuts(hist: np.ndarray, lo: float, hi: float, n_parts: int, weights: np.ndarray | None = None) -> np.ndarray:
+    """Cut coordinates (float32, length n_parts + 1) such that every part holds ~ the same number of points -- or, with `weights`
+    (one value per bin, e.g. cost_weights(hist)), the same share of the weight.
     hist: global histogram over n_bins equal bins of [lo, hi).  cuts[0] = -inf, cuts[-1] = +inf; inner cuts lie on bin edges."""
-    hist = np.asarray(hist, dtype=np.int64)
+    hist = np.asarray(hist, dtype=np.int64) if weights is None else np.asarray(weights, dtype=np.float64)
     n_bins = hist.shape[0]
-    total = int(hist.sum())
+    total = hist.sum()
     cum = np.cumsum(hist)
     cuts = np.empty(n_parts + 1, dtype=np.float32)
     cuts[0], cuts[-1] = -np.inf, np.inf
     width = (float(hi) - float(lo)) / n_bins
     prev = 0
     for g in range(1, n_parts):
-        target = (total * g) // n_parts
+        target = (total * g) // n_parts if weights is None else total * g / n_parts
         b = int(np.searchsorted(cum, target, side="left")) + 1      # cut after the bin that reaches the target
         b = min(max(b, prev), n_bins)
         prev = b
@@ -127,6 +138,8 @@ class ShardedSearch:
         # temporal coherence: the cuts of the previous step are kept while every rank's owned count stays within
         # `rebalance_tolerance` of the mean; any rank can request new cuts through the flag that rides on the counts exchange
         self.rebalance_tolerance = 0.10
+        self.balance = "cost"          # cut placement: "cost" (cost_weights: dense slabs get fewer points) or "count"
+        self._expected_owned = None    # owned points of this rank under the current cuts (from the histogram they were made from)
         self.n_global = 0
         self._recut = True
         self.n_recuts = 0
@@ -233,13 +246,18 @@ class ShardedSearch:
                 dist.all_reduce(self._hist, op=dist.ReduceOp.SUM)
             hist = self._hist.cpu().numpy()
             self.n_global = int(hist.sum())
-            self.cuts = balanced_cuts(hist, lo, hi, self.world)
+            self.cuts = balanced_cuts(hist, lo, hi, self.world, cost_weights(hist) if self.balance == "cost" else None)
+            # what this rank should own under these cuts: the yardstick of the re-balance request below
+            edges = np.clip(np.round((self.cuts[1:-1].astype(np.float64) - float(lo)) / ((float(hi) - float(lo)) / self.n_bins)).astype(np.int64), 0, self.n_bins)
+            edges = np.concatenate([[0], edges, [self.n_bins]])
+            self._expected_owned = int(hist[edges[self.rank]:edges[self.rank + 1]].sum())
             self.n_recuts += 1
         # 3. partition, 4. exchange (cut coordinates are open ended at both ends, so points that left the old box still have an owner)
         want = 0
         if self.n_global > 0 and self.n_owned > 0:
             mean = self.n_global / self.world
-            want = int(abs(self.n_owned - mean) > self.rebalance_tolerance * mean)     # judged on the previous step's balance
+            expect = self._expected_owned if self._expected_owned is not None else mean
+            want = int(abs(self.n_owned - expect) > self.rebalance_tolerance * mean)     # judged on the previous step's balance
         if self.exchange == "p2p":
             self.local, self.n_owned, self.n_halo, flag = self._push_exchange(points, id_base, want)
         else:
